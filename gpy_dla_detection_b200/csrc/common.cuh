@@ -1,0 +1,94 @@
+// common.cuh : host-side plumbing shared by the C-ABI translation units - error capture,
+// the library stream, launch accounting and a small RAII device buffer.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string>
+#include <vector>
+
+namespace dla {
+
+struct Runtime {
+  int device = -1;
+  bool ready = false;
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ev_begin = nullptr, ev_end = nullptr;
+  double last_kernel_ms = 0.0;
+  long long launches = 0;
+  int sm_count = 0;
+  size_t smem_optin = 0;
+};
+
+Runtime& runtime();
+void set_error(const std::string& msg);
+int fail(const std::string& msg);
+
+#define DLA_CUDA(call)                                                                         \
+  do {                                                                                         \
+    cudaError_t err__ = (call);                                                                \
+    if (err__ != cudaSuccess) {                                                                \
+      char buf__[512];                                                                         \
+      snprintf(buf__, sizeof(buf__), "CUDA error '%s' at %s:%d (%s)", cudaGetErrorString(err__), \
+               __FILE__, __LINE__, #call);                                                     \
+      return ::dla::fail(buf__);                                                               \
+    }                                                                                          \
+  } while (0)
+
+#define DLA_REQUIRE(cond, msg) \
+  do {                         \
+    if (!(cond)) return ::dla::fail(msg); \
+  } while (0)
+
+#define DLA_CHECK_READY() \
+  do {                    \
+    int rc__ = ::dla::ensure_ready(); \
+    if (rc__) return rc__; \
+  } while (0)
+
+int ensure_ready();
+
+// count a kernel launch and surface launch errors
+#define DLA_LAUNCHED()                 \
+  do {                                 \
+    ::dla::runtime().launches += 1;    \
+    DLA_CUDA(cudaGetLastError());      \
+  } while (0)
+
+template <typename T>
+struct DevBuf {
+  T* p = nullptr;
+  size_t n = 0;
+  DevBuf() = default;
+  DevBuf(const DevBuf&) = delete;
+  DevBuf& operator=(const DevBuf&) = delete;
+  ~DevBuf() { release(); }
+  void release() {
+    if (p) cudaFree(p);
+    p = nullptr;
+    n = 0;
+  }
+  cudaError_t alloc(size_t count) {
+    release();
+    if (count == 0) count = 1;
+    cudaError_t e = cudaMalloc(&p, count * sizeof(T));
+    if (e == cudaSuccess) n = count;
+    return e;
+  }
+  cudaError_t ensure(size_t count) { return count <= n ? cudaSuccess : alloc(count); }
+  cudaError_t upload(const T* host, size_t count, cudaStream_t s) {
+    return cudaMemcpyAsync(p, host, count * sizeof(T), cudaMemcpyHostToDevice, s);
+  }
+  cudaError_t download(T* host, size_t count, cudaStream_t s) const {
+    return cudaMemcpyAsync(host, p, count * sizeof(T), cudaMemcpyDeviceToHost, s);
+  }
+};
+
+// bracket the kernels of one API call with events on the library stream
+struct KernelTimer {
+  bool active = false;
+  cudaError_t begin();
+  cudaError_t end();  // synchronises the stream and stores runtime().last_kernel_ms
+};
+
+}  // namespace dla

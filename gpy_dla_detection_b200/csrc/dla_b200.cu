@@ -1,0 +1,793 @@
+// dla_b200.cu : C-ABI of libdla_b200.so (see include/dla_b200.h).
+// Single translation unit: the kernels live in the *.cuh headers next to this file.
+#include "../../include/dla_b200.h"
+
+#include <math.h>
+#include <string.h>
+
+#include <algorithm>
+#include <limits>
+#include <memory>
+#include <string>
+#include <vector>
+
+#include "common.cuh"
+#include "evidence_kernel.cuh"
+#include "likelihood_kernel.cuh"
+#include "prep_kernel.cuh"
+#include "voigt_kernel.cuh"
+
+namespace dla {
+
+// ------------------------------------------------------------------------------------------
+// runtime
+// ------------------------------------------------------------------------------------------
+static thread_local std::string t_error;
+Runtime& runtime() {
+  static Runtime rt;
+  return rt;
+}
+void set_error(const std::string& msg) { t_error = msg; }
+int fail(const std::string& msg) {
+  t_error = msg;
+  return 1;
+}
+
+static int init_device(int device) {
+  Runtime& rt = runtime();
+  int count = 0;
+  cudaError_t e = cudaGetDeviceCount(&count);
+  if (e != cudaSuccess || count == 0)
+    return fail(std::string("no usable CUDA device (") + cudaGetErrorString(e) +
+                "); libdla_b200 has no CPU fallback");
+  if (device < 0 || device >= count) return fail("dla_init: device index out of range");
+  if (rt.ready && rt.device == device) return 0;
+  DLA_CUDA(cudaSetDevice(device));
+  cudaDeviceProp prop;
+  DLA_CUDA(cudaGetDeviceProperties(&prop, device));
+  if (prop.major < 10) return fail(std::string("device '") + prop.name + "' is not sm_100-class; this library is built for sm_100a only");
+  if (rt.stream) {
+    cudaStreamDestroy(rt.stream);
+    cudaEventDestroy(rt.ev_begin);
+    cudaEventDestroy(rt.ev_end);
+  }
+  DLA_CUDA(cudaStreamCreateWithFlags(&rt.stream, cudaStreamNonBlocking));
+  DLA_CUDA(cudaEventCreate(&rt.ev_begin));
+  DLA_CUDA(cudaEventCreate(&rt.ev_end));
+  rt.device = device;
+  rt.sm_count = prop.multiProcessorCount;
+  rt.smem_optin = prop.sharedMemPerBlockOptin;
+
+  // pair tables of the likelihood kernel
+  uint8_t pi[LK_NBLK_PAIR * 8], pj[LK_NBLK_PAIR * 8];
+  memset(pi, 0, sizeof(pi));
+  memset(pj, 0, sizeof(pj));
+  int c = 0;
+  for (int i = 0; i < LK_K; ++i)
+    for (int j = 0; j <= i; ++j, ++c) {
+      pi[c] = (uint8_t)i;
+      pj[c] = (uint8_t)j;
+    }
+  DLA_CUDA(cudaMemcpyToSymbol(c_pair_i, pi, sizeof(pi)));
+  DLA_CUDA(cudaMemcpyToSymbol(c_pair_j, pj, sizeof(pj)));
+  DLA_CUDA(cudaFuncSetAttribute(sample_likelihood_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LK_SMEM_BYTES));
+  DLA_CUDA(cudaFuncSetAttribute(voigt_profile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rt.smem_optin));
+  rt.ready = true;
+  return 0;
+}
+
+int ensure_ready() {
+  Runtime& rt = runtime();
+  if (rt.ready) {
+    cudaError_t e = cudaSetDevice(rt.device);
+    if (e != cudaSuccess) return fail(std::string("cudaSetDevice failed: ") + cudaGetErrorString(e));
+    return 0;
+  }
+  return init_device(0);
+}
+
+cudaError_t KernelTimer::begin() {
+  active = true;
+  return cudaEventRecord(runtime().ev_begin, runtime().stream);
+}
+cudaError_t KernelTimer::end() {
+  Runtime& rt = runtime();
+  cudaError_t e = cudaEventRecord(rt.ev_end, rt.stream);
+  if (e != cudaSuccess) return e;
+  e = cudaEventSynchronize(rt.ev_end);
+  if (e != cudaSuccess) return e;
+  float ms = 0.f;
+  e = cudaEventElapsedTime(&ms, rt.ev_begin, rt.ev_end);
+  rt.last_kernel_ms = ms;
+  active = false;
+  return e;
+}
+
+// small fill kernels
+__global__ void fill_double_kernel(double* p, size_t n, double value) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) p[i] = value;
+}
+__global__ void fill_rows_kernel(int32_t* rows, int S, int nrows) {
+  // row 0 = identity (the sample's own profile); rows 1.. = resampled indices, zero-initialised
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < (size_t)S * nrows) rows[i] = i < (size_t)S ? (int32_t)i : 0;
+}
+__global__ void product_rows_kernel(const double* cache, int ld, int n, int nrows, double* out) {
+  const int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= n) return;
+  double a = cache[p];
+  for (int r = 1; r < nrows; ++r) a = a * cache[(size_t)r * ld + p];
+  out[p] = a;
+}
+__global__ void keep_to_uidx_kernel(const uint8_t* keep, int n_u, int32_t* uidx) {
+  // single thread: tiny; builds the compaction map from a keep-mask
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    int q = 0;
+    for (int i = 0; i < n_u; ++i)
+      if (keep[i]) uidx[q++] = i;
+  }
+}
+
+static inline size_t round_up(size_t a, size_t b) { return (a + b - 1) / b * b; }
+
+}  // namespace dla
+
+using namespace dla;
+
+// ------------------------------------------------------------------------------------------
+// handles
+// ------------------------------------------------------------------------------------------
+struct dla_model {
+  DevBuf<double> rest, mu, M, log_omega;
+  ModelDev dev;
+};
+
+struct dla_spectrum {
+  int n_raw = 0, n_u = 0, n = 0, k = 0, width = 0, broadening = 1, n_abs = 0, ld = 0;
+  double z_qso = 0.0;
+  double scalars[8] = {0};
+  bool from_raw = false;
+  // raw-side buffers
+  DevBuf<double> X, Y, V, scratch;
+  DevBuf<uint8_t> mask, ind_unmasked, ind;
+  // prepared arrays
+  DevBuf<double> x, y, v, this_wl, mu, omega2, M, unmasked_wl, wl_abs, padded_wl, d_scalars;
+  DevBuf<int32_t> uidx;
+  // work buffers (grown on demand)
+  DevBuf<double> cache, z_dev, nhi_dev, uniforms, raw_ll, sample_ll, log_ev, cdf;
+  DevBuf<int32_t> rows;
+  DevBuf<int> alive;
+  DevBuf<LikelihoodSpectrum> lk_desc;
+  DevBuf<EvidenceLevel> ev_desc;
+  DevBuf<AbsorptionGrid> grid_desc;
+};
+
+// ------------------------------------------------------------------------------------------
+// launch helpers (single spectrum = batch of one)
+// ------------------------------------------------------------------------------------------
+static int launch_voigt(dla_spectrum* sp, const double* d_z, const double* d_nhi, int num_samples, int num_lines,
+                        double* d_out, int ld) {
+  Runtime& rt = runtime();
+  DLA_REQUIRE(num_lines >= 1 && num_lines <= LYMAN_NUM_LINES, "num_lines must be in [1, 31]");
+  AbsorptionGrid g;
+  g.wl = sp->wl_abs.p;
+  g.uidx = sp->uidx.p;
+  g.out = d_out;
+  g.n_in = sp->n_abs;
+  g.n_out = sp->n;
+  g.ld = ld;
+  g.num_samples = num_samples;
+  g.z = d_z;
+  g.nhi = d_nhi;
+  DLA_CUDA(sp->grid_desc.ensure(1));
+  DLA_CUDA(cudaMemcpyAsync(sp->grid_desc.p, &g, sizeof(g), cudaMemcpyHostToDevice, rt.stream));
+  const int smem_row = (int)round_up((size_t)sp->n_abs + 32, 2);
+  int warps = 8;
+  while (warps > 1 && (size_t)warps * smem_row * sizeof(double) > rt.smem_optin) warps >>= 1;
+  DLA_REQUIRE((size_t)warps * smem_row * sizeof(double) <= rt.smem_optin, "absorption grid too long for shared memory");
+  dim3 grid((num_samples + warps - 1) / warps, 1);
+  voigt_profile_kernel<<<grid, warps * 32, (size_t)warps * smem_row * sizeof(double), rt.stream>>>(
+      sp->grid_desc.p, num_lines, sp->broadening, smem_row);
+  DLA_LAUNCHED();
+  return 0;
+}
+
+static int ensure_cache(dla_spectrum* sp, size_t rows) {
+  DLA_CUDA(sp->cache.ensure(rows * (size_t)sp->ld));
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------
+// library / device
+// ------------------------------------------------------------------------------------------
+extern "C" int dla_init(int device) { return init_device(device); }
+
+extern "C" int dla_device_count(void) {
+  int count = 0;
+  if (cudaGetDeviceCount(&count) != cudaSuccess) return 0;
+  return count;
+}
+
+extern "C" const char* dla_last_error(void) { return t_error.c_str(); }
+extern "C" const char* dla_version(void) { return "dla_b200 0.1 (sm_100a)"; }
+extern "C" double dla_last_kernel_ms(void) { return runtime().last_kernel_ms; }
+extern "C" long long dla_kernel_launch_count(void) { return runtime().launches; }
+
+// ------------------------------------------------------------------------------------------
+// a1: voigt
+// ------------------------------------------------------------------------------------------
+extern "C" int dla_voigt_absorption_batch(const double* wavelengths, int n_in, const double* nhis,
+                                          const double* z_dlas, int S, int num_lines, int broadening, double* out) {
+  DLA_CHECK_READY();
+  Runtime& rt = runtime();
+  DLA_REQUIRE(wavelengths && nhis && z_dlas && out, "null pointer argument");
+  const int n_out = broadening ? n_in - 2 * INSTRUMENT_WIDTH : n_in;
+  DLA_REQUIRE(n_out >= 1 && S >= 1, "voigt_absorption: need at least 7 wavelengths with broadening and S >= 1");
+  dla_spectrum sp;
+  sp.n_abs = n_in;
+  sp.n = n_out;
+  sp.broadening = broadening ? 1 : 0;
+  sp.ld = n_out;
+  DLA_CUDA(sp.wl_abs.alloc(n_in));
+  DLA_CUDA(sp.wl_abs.upload(wavelengths, n_in, rt.stream));
+  std::vector<int32_t> iota(n_out);
+  for (int i = 0; i < n_out; ++i) iota[i] = i;
+  DLA_CUDA(sp.uidx.alloc(n_out));
+  DLA_CUDA(sp.uidx.upload(iota.data(), n_out, rt.stream));
+  DLA_CUDA(sp.z_dev.alloc(S));
+  DLA_CUDA(sp.nhi_dev.alloc(S));
+  DLA_CUDA(sp.z_dev.upload(z_dlas, S, rt.stream));
+  DLA_CUDA(sp.nhi_dev.upload(nhis, S, rt.stream));
+  DLA_CUDA(sp.cache.alloc((size_t)S * n_out));
+  KernelTimer timer;
+  DLA_CUDA(timer.begin());
+  int rc = launch_voigt(&sp, sp.z_dev.p, sp.nhi_dev.p, S, num_lines, sp.cache.p, n_out);
+  if (rc) return rc;
+  DLA_CUDA(timer.end());
+  DLA_CUDA(sp.cache.download(out, (size_t)S * n_out, rt.stream));
+  DLA_CUDA(cudaStreamSynchronize(rt.stream));
+  return 0;
+}
+
+extern "C" int dla_voigt_absorption(const double* wavelengths, int n_in, double nhi, double z_dla, int num_lines,
+                                    int broadening, double* out) {
+  return dla_voigt_absorption_batch(wavelengths, n_in, &nhi, &z_dla, 1, num_lines, broadening, out);
+}
+
+extern "C" int dla_faddeeva_re(const double* x, const double* y, int n, double* out) {
+  DLA_CHECK_READY();
+  Runtime& rt = runtime();
+  DLA_REQUIRE(x && y && out && n >= 1, "bad argument");
+  DevBuf<double> dx, dy, dout;
+  DLA_CUDA(dx.alloc(n));
+  DLA_CUDA(dy.alloc(n));
+  DLA_CUDA(dout.alloc(n));
+  DLA_CUDA(dx.upload(x, n, rt.stream));
+  DLA_CUDA(dy.upload(y, n, rt.stream));
+  faddeeva_kernel<<<(n + 255) / 256, 256, 0, rt.stream>>>(dx.p, dy.p, dout.p, n);
+  DLA_LAUNCHED();
+  DLA_CUDA(dout.download(out, n, rt.stream));
+  DLA_CUDA(cudaStreamSynchronize(rt.stream));
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------
+// a2: effective optical depth
+// ------------------------------------------------------------------------------------------
+extern "C" int dla_effective_optical_depth(const double* wavelengths, int n, double beta, double tau_0, double z_qso,
+                                           int num_forest_lines, double* out) {
+  DLA_CHECK_READY();
+  Runtime& rt = runtime();
+  DLA_REQUIRE(wavelengths && out && n >= 1, "bad argument");
+  DLA_REQUIRE(num_forest_lines >= 1 && num_forest_lines <= LYMAN_NUM_LINES, "num_forest_lines must be in [1, 31]");
+  DevBuf<double> dw, dout;
+  const size_t total = (size_t)n * num_forest_lines;
+  DLA_CUDA(dw.alloc(n));
+  DLA_CUDA(dout.alloc(total));
+  DLA_CUDA(dw.upload(wavelengths, n, rt.stream));
+  effective_optical_depth_kernel<<<(unsigned)((total + 255) / 256), 256, 0, rt.stream>>>(dw.p, n, beta, tau_0, z_qso,
+                                                                                       num_forest_lines, dout.p);
+  DLA_LAUNCHED();
+  DLA_CUDA(dout.download(out, total, rt.stream));
+  DLA_CUDA(cudaStreamSynchronize(rt.stream));
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------
+// a5: generic low-rank mvn
+// ------------------------------------------------------------------------------------------
+extern "C" int dla_log_mvnpdf_low_rank(const double* y, const double* mu, const double* M, const double* d, int n, int k,
+                                       double* out) {
+  DLA_CHECK_READY();
+  Runtime& rt = runtime();
+  DLA_REQUIRE(y && mu && M && d && out, "null pointer argument");
+  DLA_REQUIRE(n >= 1 && k >= 1 && k <= LG_MAXK, "log_mvnpdf_low_rank: need n >= 1 and 1 <= k <= 64");
+  DevBuf<double> dy, dmu, dM, dd, dout;
+  DLA_CUDA(dy.alloc(n));
+  DLA_CUDA(dmu.alloc(n));
+  DLA_CUDA(dM.alloc((size_t)n * k));
+  DLA_CUDA(dd.alloc(n));
+  DLA_CUDA(dout.alloc(1));
+  DLA_CUDA(dy.upload(y, n, rt.stream));
+  DLA_CUDA(dmu.upload(mu, n, rt.stream));
+  DLA_CUDA(dM.upload(M, (size_t)n * k, rt.stream));
+  DLA_CUDA(dd.upload(d, n, rt.stream));
+  log_mvnpdf_low_rank_kernel<<<1, 256, 0, rt.stream>>>(dy.p, dmu.p, dM.p, dd.p, n, k, dout.p);
+  DLA_LAUNCHED();
+  DLA_CUDA(dout.download(out, 1, rt.stream));
+  DLA_CUDA(cudaStreamSynchronize(rt.stream));
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------
+// a4: model
+// ------------------------------------------------------------------------------------------
+extern "C" int dla_model_create(const double* rest_wavelengths, const double* mu, const double* M,
+                                const double* log_omega, int n_rest, int k, double log_c_0, double log_tau_0,
+                                double log_beta, double prev_tau_0, double prev_beta, dla_model** out) {
+  DLA_CHECK_READY();
+  Runtime& rt = runtime();
+  DLA_REQUIRE(rest_wavelengths && mu && M && log_omega && out, "null pointer argument");
+  DLA_REQUIRE(n_rest >= 2 && k >= 1, "model needs at least two grid points");
+  std::unique_ptr<dla_model> m(new dla_model());
+  DLA_CUDA(m->rest.alloc(n_rest));
+  DLA_CUDA(m->mu.alloc(n_rest));
+  DLA_CUDA(m->M.alloc((size_t)n_rest * k));
+  DLA_CUDA(m->log_omega.alloc(n_rest));
+  DLA_CUDA(m->rest.upload(rest_wavelengths, n_rest, rt.stream));
+  DLA_CUDA(m->mu.upload(mu, n_rest, rt.stream));
+  DLA_CUDA(m->M.upload(M, (size_t)n_rest * k, rt.stream));
+  DLA_CUDA(m->log_omega.upload(log_omega, n_rest, rt.stream));
+  DLA_CUDA(cudaStreamSynchronize(rt.stream));
+  m->dev.rest_wavelengths = m->rest.p;
+  m->dev.mu = m->mu.p;
+  m->dev.M = m->M.p;
+  m->dev.log_omega = m->log_omega.p;
+  m->dev.n_rest = n_rest;
+  m->dev.k = k;
+  m->dev.log_c_0 = log_c_0;
+  m->dev.log_tau_0 = log_tau_0;
+  m->dev.log_beta = log_beta;
+  m->dev.prev_tau_0 = prev_tau_0;
+  m->dev.prev_beta = prev_beta;
+  *out = m.release();
+  return 0;
+}
+
+extern "C" int dla_model_destroy(dla_model* model) {
+  delete model;
+  return 0;
+}
+
+static PrepParams to_prep_params(const dla_params* p, int normalize) {
+  PrepParams P;
+  P.min_lambda = p->min_lambda;
+  P.max_lambda = p->max_lambda;
+  P.norm_min_lambda = p->normalization_min_lambda;
+  P.norm_max_lambda = p->normalization_max_lambda;
+  P.pixel_spacing = p->pixel_spacing;
+  P.lya_wavelength = p->lya_wavelength;
+  P.lyman_limit = p->lyman_limit;
+  P.max_z_cut = p->max_z_cut;
+  P.min_z_cut = p->min_z_cut;
+  P.width = p->width;
+  P.num_forest_lines = p->num_forest_lines;
+  P.broadening = p->broadening;
+  P.normalize = normalize;
+  return P;
+}
+
+// ------------------------------------------------------------------------------------------
+// a3/a4: spectrum preparation
+// ------------------------------------------------------------------------------------------
+extern "C" int dla_spectrum_create(const dla_model* model, const dla_params* params, const double* X, const double* Y,
+                                   const double* V, const uint8_t* pixel_mask, int n_raw, double z_qso, int normalize,
+                                   dla_spectrum** out) {
+  DLA_CHECK_READY();
+  Runtime& rt = runtime();
+  DLA_REQUIRE(model && params && X && Y && V && pixel_mask && out, "null pointer argument");
+  DLA_REQUIRE(n_raw >= 1, "empty spectrum");
+  DLA_REQUIRE(params->width == INSTRUMENT_WIDTH, "instrument profile width must be 3");
+  DLA_REQUIRE(params->num_forest_lines >= 1 && params->num_forest_lines <= LYMAN_NUM_LINES,
+              "num_forest_lines must be in [1, 31]");
+  std::unique_ptr<dla_spectrum> sp(new dla_spectrum());
+  const int w = params->width;
+  const int k = model->dev.k;
+  sp->n_raw = n_raw;
+  sp->k = k;
+  sp->width = w;
+  sp->broadening = params->broadening ? 1 : 0;
+  sp->z_qso = z_qso;
+  sp->from_raw = true;
+  DLA_CUDA(sp->X.alloc(n_raw));
+  DLA_CUDA(sp->Y.alloc(n_raw));
+  DLA_CUDA(sp->V.alloc(n_raw));
+  DLA_CUDA(sp->mask.alloc(n_raw));
+  DLA_CUDA(sp->scratch.alloc(n_raw));
+  DLA_CUDA(sp->ind_unmasked.alloc(n_raw));
+  DLA_CUDA(sp->ind.alloc(n_raw));
+  DLA_CUDA(sp->x.alloc(n_raw));
+  DLA_CUDA(sp->y.alloc(n_raw));
+  DLA_CUDA(sp->v.alloc(n_raw));
+  DLA_CUDA(sp->this_wl.alloc(n_raw));
+  DLA_CUDA(sp->mu.alloc(n_raw));
+  DLA_CUDA(sp->omega2.alloc(n_raw));
+  DLA_CUDA(sp->M.alloc((size_t)n_raw * k));
+  DLA_CUDA(sp->uidx.alloc(n_raw));
+  DLA_CUDA(sp->unmasked_wl.alloc(n_raw));
+  DLA_CUDA(sp->wl_abs.alloc(n_raw + 2 * w));
+  DLA_CUDA(sp->padded_wl.alloc(n_raw + 2 * w));
+  DLA_CUDA(sp->d_scalars.alloc(8));
+  DLA_CUDA(sp->X.upload(X, n_raw, rt.stream));
+  DLA_CUDA(sp->Y.upload(Y, n_raw, rt.stream));
+  DLA_CUDA(sp->V.upload(V, n_raw, rt.stream));
+  DLA_CUDA(sp->mask.upload(pixel_mask, n_raw, rt.stream));
+
+  PrepTask t;
+  t.X = sp->X.p;
+  t.Wobs = nullptr;
+  t.Y = sp->Y.p;
+  t.V = sp->V.p;
+  t.mask = sp->mask.p;
+  t.n_raw = n_raw;
+  t.z_qso = z_qso;
+  t.ind_unmasked = sp->ind_unmasked.p;
+  t.ind = sp->ind.p;
+  t.x = sp->x.p;
+  t.y = sp->y.p;
+  t.v = sp->v.p;
+  t.this_wl = sp->this_wl.p;
+  t.mu = sp->mu.p;
+  t.omega2 = sp->omega2.p;
+  t.M = sp->M.p;
+  t.uidx = sp->uidx.p;
+  t.unmasked_wl = sp->unmasked_wl.p;
+  t.wl_abs = sp->wl_abs.p;
+  t.padded_wl = sp->padded_wl.p;
+  t.scratch = sp->scratch.p;
+  t.scalars = sp->d_scalars.p;
+  DevBuf<PrepTask> d_task;
+  DLA_CUDA(d_task.alloc(1));
+  DLA_CUDA(cudaMemcpyAsync(d_task.p, &t, sizeof(t), cudaMemcpyHostToDevice, rt.stream));
+  KernelTimer timer;
+  DLA_CUDA(timer.begin());
+  prepare_spectrum_kernel<<<1, 256, 0, rt.stream>>>(d_task.p, model->dev, to_prep_params(params, normalize));
+  DLA_LAUNCHED();
+  DLA_CUDA(timer.end());
+  DLA_CUDA(sp->d_scalars.download(sp->scalars, 8, rt.stream));
+  DLA_CUDA(cudaStreamSynchronize(rt.stream));
+  sp->n_u = (int)sp->scalars[0];
+  sp->n = (int)sp->scalars[1];
+  sp->n_abs = sp->broadening ? sp->n_u + 2 * w : sp->n_u;
+  sp->ld = (int)round_up(std::max(sp->n, 1), 4);
+  *out = sp.release();
+  return 0;
+}
+
+extern "C" int dla_spectrum_create_prepared(const double* y, const double* v, const double* mu, const double* M,
+                                            const double* omega2, int n, int k, const double* wl_abs, int n_abs,
+                                            const uint8_t* keep, int n_u, int broadening, dla_spectrum** out) {
+  DLA_CHECK_READY();
+  Runtime& rt = runtime();
+  DLA_REQUIRE(y && v && mu && M && omega2 && wl_abs && keep && out, "null pointer argument");
+  DLA_REQUIRE(n >= 1 && k >= 1, "empty spectrum");
+  DLA_REQUIRE(n_abs == (broadening ? n_u + 2 * INSTRUMENT_WIDTH : n_u), "absorption grid length does not match n_u");
+  int kept = 0;
+  for (int i = 0; i < n_u; ++i) kept += keep[i] ? 1 : 0;
+  DLA_REQUIRE(kept == n, "keep mask does not select n pixels");  // dla_gp.py:390 assert
+  std::unique_ptr<dla_spectrum> sp(new dla_spectrum());
+  sp->n = n;
+  sp->n_u = n_u;
+  sp->k = k;
+  sp->width = INSTRUMENT_WIDTH;
+  sp->broadening = broadening ? 1 : 0;
+  sp->n_abs = n_abs;
+  sp->ld = (int)round_up(n, 4);
+  DLA_CUDA(sp->y.alloc(n));
+  DLA_CUDA(sp->v.alloc(n));
+  DLA_CUDA(sp->mu.alloc(n));
+  DLA_CUDA(sp->omega2.alloc(n));
+  DLA_CUDA(sp->M.alloc((size_t)n * k));
+  DLA_CUDA(sp->wl_abs.alloc(n_abs));
+  DLA_CUDA(sp->uidx.alloc(n));
+  DLA_CUDA(sp->y.upload(y, n, rt.stream));
+  DLA_CUDA(sp->v.upload(v, n, rt.stream));
+  DLA_CUDA(sp->mu.upload(mu, n, rt.stream));
+  DLA_CUDA(sp->omega2.upload(omega2, n, rt.stream));
+  DLA_CUDA(sp->M.upload(M, (size_t)n * k, rt.stream));
+  DLA_CUDA(sp->wl_abs.upload(wl_abs, n_abs, rt.stream));
+  std::vector<int32_t> uidx;
+  uidx.reserve(n);
+  for (int i = 0; i < n_u; ++i)
+    if (keep[i]) uidx.push_back(i);
+  DLA_CUDA(sp->uidx.upload(uidx.data(), n, rt.stream));
+  DLA_CUDA(cudaStreamSynchronize(rt.stream));
+  *out = sp.release();
+  return 0;
+}
+
+extern "C" int dla_spectrum_destroy(dla_spectrum* spec) {
+  delete spec;
+  return 0;
+}
+
+extern "C" int dla_spectrum_sizes(const dla_spectrum* spec, int* n_raw, int* n_u, int* n) {
+  DLA_REQUIRE(spec, "null spectrum");
+  if (n_raw) *n_raw = spec->n_raw;
+  if (n_u) *n_u = spec->n_u;
+  if (n) *n = spec->n;
+  return 0;
+}
+
+extern "C" int dla_spectrum_get(const dla_spectrum* sp, double* x, double* y, double* v, double* this_wavelengths,
+                                double* this_mu, double* this_M, double* this_omega2, double* unmasked_wavelengths,
+                                double* padded_wavelengths, uint8_t* ind_unmasked, uint8_t* ind,
+                                double* normalization_median) {
+  DLA_CHECK_READY();
+  Runtime& rt = runtime();
+  DLA_REQUIRE(sp, "null spectrum");
+  const size_t n = sp->n, nu = sp->n_u;
+  if (x && sp->x.p) DLA_CUDA(sp->x.download(x, n, rt.stream));
+  if (y) DLA_CUDA(sp->y.download(y, n, rt.stream));
+  if (v) DLA_CUDA(sp->v.download(v, n, rt.stream));
+  if (this_wavelengths && sp->this_wl.p) DLA_CUDA(sp->this_wl.download(this_wavelengths, n, rt.stream));
+  if (this_mu) DLA_CUDA(sp->mu.download(this_mu, n, rt.stream));
+  if (this_M) DLA_CUDA(sp->M.download(this_M, n * sp->k, rt.stream));
+  if (this_omega2) DLA_CUDA(sp->omega2.download(this_omega2, n, rt.stream));
+  if (unmasked_wavelengths && sp->unmasked_wl.p) DLA_CUDA(sp->unmasked_wl.download(unmasked_wavelengths, nu, rt.stream));
+  if (padded_wavelengths && sp->padded_wl.p)
+    DLA_CUDA(sp->padded_wl.download(padded_wavelengths, nu + 2 * sp->width, rt.stream));
+  if (ind_unmasked && sp->ind_unmasked.p) DLA_CUDA(sp->ind_unmasked.download(ind_unmasked, sp->n_raw, rt.stream));
+  if (ind && sp->ind.p) DLA_CUDA(sp->ind.download(ind, sp->n_raw, rt.stream));
+  DLA_CUDA(cudaStreamSynchronize(rt.stream));
+  if (normalization_median) *normalization_median = sp->scalars[2];
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------
+// likelihood launches on one spectrum
+// ------------------------------------------------------------------------------------------
+static LikelihoodSpectrum base_desc(dla_spectrum* sp) {
+  LikelihoodSpectrum d;
+  d.y = sp->y.p;
+  d.v = sp->v.p;
+  d.mu = sp->mu.p;
+  d.omega2 = sp->omega2.p;
+  d.M = sp->M.p;
+  d.cache = sp->cache.p;
+  d.rows = nullptr;
+  d.out = nullptr;
+  d.n = sp->n;
+  d.ld = sp->ld;
+  d.num_samples = 0;
+  d.num_rows = 1;
+  d.row_stride = 0;
+  d.row0 = 0;
+  d.alive = nullptr;
+  return d;
+}
+
+static int launch_likelihood(const LikelihoodSpectrum* d_desc, int max_samples, int num_spectra) {
+  Runtime& rt = runtime();
+  dim3 grid((max_samples + LK_TS - 1) / LK_TS, num_spectra);
+  sample_likelihood_kernel<<<grid, LK_THREADS, LK_SMEM_BYTES, rt.stream>>>(d_desc);
+  DLA_LAUNCHED();
+  return 0;
+}
+
+extern "C" int dla_null_log_model_evidence(dla_spectrum* sp, double* out) {
+  DLA_CHECK_READY();
+  Runtime& rt = runtime();
+  DLA_REQUIRE(sp && out, "null pointer argument");
+  DLA_REQUIRE(sp->k == LK_K, "the batched likelihood path is built for k = 20");
+  DLA_REQUIRE(sp->n >= 1, "spectrum has no modelled pixels");
+  DevBuf<double> ones, res;
+  DLA_CUDA(ones.alloc(sp->ld));
+  DLA_CUDA(res.alloc(1));
+  KernelTimer timer;
+  DLA_CUDA(timer.begin());
+  fill_double_kernel<<<(sp->ld + 255) / 256, 256, 0, rt.stream>>>(ones.p, sp->ld, 1.0);
+  DLA_LAUNCHED();
+  LikelihoodSpectrum d = base_desc(sp);
+  d.cache = ones.p;
+  d.out = res.p;
+  d.num_samples = 1;
+  DLA_CUDA(sp->lk_desc.ensure(16));
+  DLA_CUDA(cudaMemcpyAsync(sp->lk_desc.p, &d, sizeof(d), cudaMemcpyHostToDevice, rt.stream));
+  int rc = launch_likelihood(sp->lk_desc.p, 1, 1);
+  if (rc) return rc;
+  DLA_CUDA(timer.end());
+  DLA_CUDA(res.download(out, 1, rt.stream));
+  DLA_CUDA(cudaStreamSynchronize(rt.stream));
+  return 0;
+}
+
+extern "C" int dla_sample_log_likelihoods(dla_spectrum* sp, const double* z_dlas, const double* nhis, int S, int k_dlas,
+                                          int num_lines, double* out) {
+  DLA_CHECK_READY();
+  Runtime& rt = runtime();
+  DLA_REQUIRE(sp && z_dlas && nhis && out, "null pointer argument");
+  DLA_REQUIRE(S >= 1 && k_dlas >= 1 && k_dlas <= LK_MAX_ROWS, "need S >= 1 and 1 <= k_dlas <= 8");
+  DLA_REQUIRE(sp->k == LK_K, "the batched likelihood path is built for k = 20");
+  DLA_REQUIRE(sp->n >= 1, "spectrum has no modelled pixels");
+  const size_t rows = (size_t)S * k_dlas;
+  // factor r of sample s lives in profile row r*S + s
+  std::vector<double> zt(rows), nt(rows);
+  for (int s = 0; s < S; ++s)
+    for (int r = 0; r < k_dlas; ++r) {
+      zt[(size_t)r * S + s] = z_dlas[(size_t)s * k_dlas + r];
+      nt[(size_t)r * S + s] = nhis[(size_t)s * k_dlas + r];
+    }
+  DLA_CUDA(sp->z_dev.ensure(rows));
+  DLA_CUDA(sp->nhi_dev.ensure(rows));
+  DLA_CUDA(sp->z_dev.upload(zt.data(), rows, rt.stream));
+  DLA_CUDA(sp->nhi_dev.upload(nt.data(), rows, rt.stream));
+  int rc = ensure_cache(sp, rows);
+  if (rc) return rc;
+  DLA_CUDA(sp->raw_ll.ensure(S));
+  KernelTimer timer;
+  DLA_CUDA(timer.begin());
+  rc = launch_voigt(sp, sp->z_dev.p, sp->nhi_dev.p, (int)rows, num_lines, sp->cache.p, sp->ld);
+  if (rc) return rc;
+  LikelihoodSpectrum d = base_desc(sp);
+  d.out = sp->raw_ll.p;
+  d.num_samples = S;
+  d.num_rows = k_dlas;
+  d.row_stride = S;
+  DLA_CUDA(sp->lk_desc.ensure(16));
+  DLA_CUDA(cudaMemcpyAsync(sp->lk_desc.p, &d, sizeof(d), cudaMemcpyHostToDevice, rt.stream));
+  rc = launch_likelihood(sp->lk_desc.p, S, 1);
+  if (rc) return rc;
+  DLA_CUDA(timer.end());
+  DLA_CUDA(sp->raw_ll.download(out, S, rt.stream));
+  DLA_CUDA(cudaStreamSynchronize(rt.stream));
+  return 0;
+}
+
+extern "C" int dla_absorption_k_dlas(dla_spectrum* sp, const double* z_dlas, const double* nhis, int k_dlas,
+                                     int num_lines, double* out) {
+  DLA_CHECK_READY();
+  Runtime& rt = runtime();
+  DLA_REQUIRE(sp && z_dlas && nhis && out, "null pointer argument");
+  DLA_REQUIRE(k_dlas >= 1, "need at least one absorber");
+  DLA_REQUIRE(sp->n >= 1, "spectrum has no modelled pixels");
+  DLA_CUDA(sp->z_dev.ensure(k_dlas));
+  DLA_CUDA(sp->nhi_dev.ensure(k_dlas));
+  DLA_CUDA(sp->z_dev.upload(z_dlas, k_dlas, rt.stream));
+  DLA_CUDA(sp->nhi_dev.upload(nhis, k_dlas, rt.stream));
+  int rc = ensure_cache(sp, (size_t)k_dlas + 1);
+  if (rc) return rc;
+  rc = launch_voigt(sp, sp->z_dev.p, sp->nhi_dev.p, k_dlas, num_lines, sp->cache.p, sp->ld);
+  if (rc) return rc;
+  double* d_out = sp->cache.p + (size_t)k_dlas * sp->ld;
+  product_rows_kernel<<<(sp->n + 255) / 256, 256, 0, rt.stream>>>(sp->cache.p, sp->ld, sp->n, k_dlas, d_out);
+  DLA_LAUNCHED();
+  DLA_CUDA(cudaMemcpyAsync(out, d_out, sizeof(double) * sp->n, cudaMemcpyDeviceToHost, rt.stream));
+  DLA_CUDA(cudaStreamSynchronize(rt.stream));
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------
+// a9: evidence levels on one spectrum
+// ------------------------------------------------------------------------------------------
+extern "C" int dla_log_model_evidences(dla_spectrum* sp, const double* z_samples, const double* nhi_samples, int S,
+                                       int max_dlas, const double* uniforms, double min_z_separation, int num_lines,
+                                       double* sample_log_likelihoods, int32_t* base_sample_inds, double* log_evidences,
+                                       int* uniform_rows_used) {
+  DLA_CHECK_READY();
+  Runtime& rt = runtime();
+  DLA_REQUIRE(sp && z_samples && nhi_samples && log_evidences, "null pointer argument");
+  DLA_REQUIRE(S >= 1 && max_dlas >= 1 && max_dlas <= LK_MAX_ROWS, "need S >= 1 and 1 <= max_dlas <= 8");
+  DLA_REQUIRE(max_dlas == 1 || uniforms, "uniforms are required when max_dlas > 1");
+  DLA_REQUIRE(sp->k == LK_K, "the batched likelihood path is built for k = 20");
+  DLA_REQUIRE(sp->n >= 1, "spectrum has no modelled pixels");
+
+  DLA_CUDA(sp->z_dev.ensure(S));
+  DLA_CUDA(sp->nhi_dev.ensure(S));
+  DLA_CUDA(sp->z_dev.upload(z_samples, S, rt.stream));
+  DLA_CUDA(sp->nhi_dev.upload(nhi_samples, S, rt.stream));
+  if (max_dlas > 1) {
+    DLA_CUDA(sp->uniforms.ensure((size_t)(max_dlas - 1) * S));
+    DLA_CUDA(sp->uniforms.upload(uniforms, (size_t)(max_dlas - 1) * S, rt.stream));
+  }
+  int rc = ensure_cache(sp, S);
+  if (rc) return rc;
+  DLA_CUDA(sp->raw_ll.ensure(S));
+  DLA_CUDA(sp->sample_ll.ensure((size_t)S * max_dlas));
+  DLA_CUDA(sp->log_ev.ensure(max_dlas));
+  DLA_CUDA(sp->cdf.ensure(S));
+  DLA_CUDA(sp->rows.ensure((size_t)S * max_dlas));
+  DLA_CUDA(sp->alive.ensure(2));
+  DLA_CUDA(sp->lk_desc.ensure(16));
+  DLA_CUDA(sp->ev_desc.ensure(16));
+
+  // descriptors of all levels (they do not depend on results)
+  std::vector<LikelihoodSpectrum> lk(max_dlas);
+  std::vector<EvidenceLevel> ev(max_dlas);
+  for (int level = 0; level < max_dlas; ++level) {
+    LikelihoodSpectrum d = base_desc(sp);
+    d.out = sp->raw_ll.p;
+    d.num_samples = S;
+    d.num_rows = level + 1;
+    d.rows = sp->rows.p;
+    d.row_stride = S;
+    d.alive = sp->alive.p;
+    lk[level] = d;
+    EvidenceLevel e;
+    e.raw_ll = sp->raw_ll.p;
+    e.sample_ll = sp->sample_ll.p + level;
+    e.ll_stride = max_dlas;
+    e.z_samples = sp->z_dev.p;
+    e.base_inds = sp->rows.p + S;
+    e.base_out = (level + 1 < max_dlas) ? sp->rows.p + (size_t)(level + 1) * S : nullptr;
+    e.uniforms = (level + 1 < max_dlas) ? sp->uniforms.p + (size_t)level * S : nullptr;
+    e.log_evidence = sp->log_ev.p + level;
+    e.cdf_scratch = sp->cdf.p;
+    e.alive = sp->alive.p;
+    e.status = sp->alive.p + 1;
+    e.S = S;
+    e.level = level;
+    e.min_z_separation = min_z_separation;
+    ev[level] = e;
+  }
+  DLA_CUDA(cudaMemcpyAsync(sp->lk_desc.p, lk.data(), sizeof(LikelihoodSpectrum) * max_dlas, cudaMemcpyHostToDevice, rt.stream));
+  DLA_CUDA(cudaMemcpyAsync(sp->ev_desc.p, ev.data(), sizeof(EvidenceLevel) * max_dlas, cudaMemcpyHostToDevice, rt.stream));
+  const int alive_init[2] = {1, 0};
+  DLA_CUDA(cudaMemcpyAsync(sp->alive.p, alive_init, sizeof(alive_init), cudaMemcpyHostToDevice, rt.stream));
+
+  KernelTimer timer;
+  DLA_CUDA(timer.begin());
+  const double nan = std::numeric_limits<double>::quiet_NaN();
+  fill_double_kernel<<<(unsigned)(((size_t)S * max_dlas + 255) / 256), 256, 0, rt.stream>>>(sp->sample_ll.p, (size_t)S * max_dlas, nan);
+  DLA_LAUNCHED();
+  fill_double_kernel<<<1, 256, 0, rt.stream>>>(sp->log_ev.p, max_dlas, nan);
+  DLA_LAUNCHED();
+  fill_rows_kernel<<<(unsigned)(((size_t)S * max_dlas + 255) / 256), 256, 0, rt.stream>>>(sp->rows.p, S, max_dlas);
+  DLA_LAUNCHED();
+  rc = launch_voigt(sp, sp->z_dev.p, sp->nhi_dev.p, S, num_lines, sp->cache.p, sp->ld);
+  if (rc) return rc;
+  for (int level = 0; level < max_dlas; ++level) {
+    rc = launch_likelihood(sp->lk_desc.p + level, S, 1);
+    if (rc) return rc;
+    evidence_level_kernel<<<1, 1024, 0, rt.stream>>>(sp->ev_desc.p + level);
+    DLA_LAUNCHED();
+  }
+  DLA_CUDA(timer.end());
+  DLA_CUDA(sp->log_ev.download(log_evidences, max_dlas, rt.stream));
+  if (sample_log_likelihoods) DLA_CUDA(sp->sample_ll.download(sample_log_likelihoods, (size_t)S * max_dlas, rt.stream));
+  if (base_sample_inds && max_dlas > 1)
+    DLA_CUDA(cudaMemcpyAsync(base_sample_inds, sp->rows.p + S, sizeof(int32_t) * (size_t)(max_dlas - 1) * S,
+                             cudaMemcpyDeviceToHost, rt.stream));
+  DLA_CUDA(cudaStreamSynchronize(rt.stream));
+  if (uniform_rows_used) {
+    int used = 0;
+    for (int level = 0; level + 1 < max_dlas; ++level) {
+      if (isnan(log_evidences[level])) break;
+      ++used;
+    }
+    *uniform_rows_used = used;
+  }
+  return 0;
+}
+
+extern "C" int dla_resample_indices(const double* W, const double* uniforms, int S, int32_t* out) {
+  DLA_CHECK_READY();
+  Runtime& rt = runtime();
+  DLA_REQUIRE(W && uniforms && out && S >= 1, "bad argument");
+  DevBuf<double> dW, dU, scratch;
+  DevBuf<int32_t> dout;
+  DLA_CUDA(dW.alloc(S));
+  DLA_CUDA(dU.alloc(S));
+  DLA_CUDA(scratch.alloc(S));
+  DLA_CUDA(dout.alloc(S));
+  DLA_CUDA(dW.upload(W, S, rt.stream));
+  DLA_CUDA(dU.upload(uniforms, S, rt.stream));
+  resample_kernel<<<1, 1024, 0, rt.stream>>>(dW.p, dU.p, S, scratch.p, dout.p);
+  DLA_LAUNCHED();
+  DLA_CUDA(dout.download(out, S, rt.stream));
+  DLA_CUDA(cudaStreamSynchronize(rt.stream));
+  return 0;
+}
+
+#include "catalogue.inc.cuh"

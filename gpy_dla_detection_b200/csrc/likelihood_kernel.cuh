@@ -1,0 +1,348 @@
+// likelihood_kernel.cuh : batched low-rank Gaussian log-likelihoods of absorber samples
+// (SURVEY.md §8 a5, a7, a8).
+//
+// Reference: for every QMC sample the Python loop builds dla_mu = mu a, dla_M = M a,
+// d = omega2 a^2 + v (dla_gp.py:388-394) and calls NullGP.log_mvnpdf_low_rank
+// (null_gp.py:307-360): B = I + M'D^-1 M (dgemm), chol(B), quad and log-det.
+//
+// Here all samples of a tile share the interpolated model, so with
+//     w_sp = a_sp^2 / d_sp ,  g_sp = a_sp r_sp / d_sp ,  r_sp = y_p - mu_p a_sp
+// the per-sample Gram matrices and projections are ONE dense FP64 contraction
+//     [B_s - I | c_s] = [W | G] x [P | M] ,   P[p,(i,j)] = m_pi m_pj  (i >= j, 210 pairs)
+// over the pixel axis, run on the FP64 tensor path (DMMA m8n8k4; B200 measures 36.9 TFLOP/s,
+// same as the DFMA pipe, at a fraction of the issue slots).  W/G tiles are produced on the
+// fly from the profile cache (product of up to 4 absorber rows, dla_gp.py:370-386), P is
+// formed in registers from the staged M tile, and the k x k Cholesky factor / solve /
+// log-det of every sample of the tile runs in shared memory straight out of the accumulator
+// fragments.  HBM sees only the profile rows (read) and one double per sample (written).
+#pragma once
+#include <stdint.h>
+
+namespace dla {
+
+constexpr int LK_K = 20;                        // rank of the learned covariance (Parameters.k)
+constexpr int LK_PAIRS = LK_K * (LK_K + 1) / 2;  // 210 lower-triangle pairs
+constexpr int LK_TS = 64;                        // samples per CTA tile
+constexpr int LK_KC = 32;                        // pixels per chunk
+constexpr int LK_WSTRIDE = LK_KC + 4;            // padded row stride of the W/G tiles (conflict-free DMMA A loads)
+constexpr int LK_MSTRIDE = LK_K;                 // row stride of the M tile (20 == 4 mod 16: conflict-free B loads)
+constexpr int LK_THREADS = 256;
+constexpr int LK_NBLK_PAIR = 27;                 // ceil(210 / 8) column blocks of the Gram part
+constexpr int LK_NBLK = 30;                      // + 3 column blocks (24 >= 20) of the projection part
+constexpr int LK_EP_COLS = 216 + 24;             // columns staged for the epilogue
+constexpr int LK_EP_STRIDE = LK_TS + 1;          // epilogue smem: [col][sample], stride 65
+constexpr int LK_MAX_ROWS = 8;                   // max absorbers multiplied per sample (max_dlas <= 8)
+constexpr double LK_LOG_2PI = 1.83787706640934534;  // null_gp.py:325
+
+// pair index c -> (i, j), i >= j, row-major lower triangle; pads map to (0,0)
+__device__ __constant__ uint8_t c_pair_i[LK_NBLK_PAIR * 8];
+__device__ __constant__ uint8_t c_pair_j[LK_NBLK_PAIR * 8];
+
+// One spectrum as the likelihood kernel sees it.
+struct LikelihoodSpectrum {
+  const double* y;       // n   normalised flux of the modelled pixels
+  const double* v;       // n   noise variance
+  const double* mu;      // n   this_mu  (mean-flux suppressed)
+  const double* omega2;  // n   this_omega2
+  const double* M;       // n x 20 row-major this_M
+  const double* cache;   // profile rows, stride ld
+  const int32_t* rows;   // [num_rows][row_stride] profile-row index of each factor, or nullptr:
+                         //   factor r of sample s is profile row row0 + r * row_stride + s
+  const int* alive;      // if non-null and *alive == 0 the spectrum left the level loop (NaN evidence): skip
+  double* out;           // num_samples raw log-likelihoods
+  int n;                 // modelled pixels
+  int ld;                // profile row stride
+  int num_samples;       // samples in this launch
+  int num_rows;          // factors per sample (1..LK_MAX_ROWS)
+  int row_stride;        // stride between factor arrays in `rows`
+  int row0;              // first profile row when rows == nullptr
+};
+
+
+__device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+               : "+d"(c0), "+d"(c1)
+               : "d"(a), "d"(b));
+}
+
+constexpr size_t LK_TILE_BYTES = (2 * LK_TS * LK_WSTRIDE + LK_KC * LK_MSTRIDE) * sizeof(double);
+constexpr size_t LK_EP_BYTES = (size_t)LK_EP_COLS * LK_EP_STRIDE * sizeof(double);
+constexpr size_t LK_AUX_BYTES = LK_TS * 2 * sizeof(double) + LK_MAX_ROWS * LK_TS * sizeof(int32_t);
+constexpr size_t LK_SMEM_BYTES = (LK_EP_BYTES > 2 * LK_TILE_BYTES ? LK_EP_BYTES : 2 * LK_TILE_BYTES) + LK_AUX_BYTES;
+
+// grid = (ceil(max num_samples / 64), num_spectra), block = 256, dynamic smem = LK_SMEM_BYTES
+__global__ void __launch_bounds__(LK_THREADS, 1)
+sample_likelihood_kernel(const LikelihoodSpectrum* __restrict__ specs) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const LikelihoodSpectrum sp = specs[blockIdx.y];
+  const int tile_s0 = blockIdx.x * LK_TS;
+  if (tile_s0 >= sp.num_samples) return;
+  if (sp.alive && *sp.alive == 0) return;
+
+  // ---- shared memory carve-up -----------------------------------------------------------
+  // main loop : 2 stages x { W[64][36], G[64][36], M[32][20] }
+  // epilogue  : E[240][65] overlays the stages
+  double* s_main = reinterpret_cast<double*>(smem_raw);
+  const size_t main_doubles = (LK_EP_BYTES > 2 * LK_TILE_BYTES ? LK_EP_BYTES : 2 * LK_TILE_BYTES) / sizeof(double);
+  double* s_sums = s_main + main_doubles;                        // [64][2] : sum r^2/d, sum log d
+  int32_t* s_rows = reinterpret_cast<int32_t*>(s_sums + LK_TS * 2);  // [num_rows][64]
+  constexpr int STAGE_DOUBLES = 2 * LK_TS * LK_WSTRIDE + LK_KC * LK_MSTRIDE;
+
+  const int tid = threadIdx.x;
+  const int warp = tid >> 5, lane = tid & 31;
+  const int n = sp.n;
+  const int nchunks = (n + LK_KC - 1) / LK_KC;
+
+  // ---- profile rows of the tile's samples -----------------------------------------------
+  for (int e = tid; e < sp.num_rows * LK_TS; e += LK_THREADS) {
+    const int r = e / LK_TS, s = e % LK_TS;
+    const int gs = tile_s0 + s;
+    int row = 0;
+    if (gs < sp.num_samples) row = sp.rows ? sp.rows[(size_t)r * sp.row_stride + gs] : sp.row0 + r * sp.row_stride + gs;
+    s_rows[r * LK_TS + s] = row;
+  }
+  __syncthreads();
+
+  // ---- MMA roles: warp = (mhalf, quarter); warp tile = 32 samples x 8 column blocks --------
+  const int mhalf = warp >> 2;    // samples [32*mhalf, 32*mhalf+32)
+  const int quarter = warp & 3;   // column blocks [8*quarter, 8*quarter+8)  (quarter 3: 24..26 pairs + 3 projection)
+  const int grp = lane >> 2;      // DMMA groupID
+  const int tig = lane & 3;       // DMMA threadID_in_group
+  // per-lane column operands: for block nb, this lane provides B[k=tig][n=grp]
+  int col_i[8], col_j[8];
+#pragma unroll
+  for (int nb = 0; nb < 8; ++nb) {
+    const int blk = quarter * 8 + nb;
+    if (blk < LK_NBLK_PAIR) {
+      col_i[nb] = c_pair_i[blk * 8 + grp];
+      col_j[nb] = c_pair_j[blk * 8 + grp];
+    } else {
+      const int j = (blk - LK_NBLK_PAIR) * 8 + grp;  // projection column (pads clamp to 0)
+      col_i[nb] = -1;
+      col_j[nb] = j < LK_K ? j : 0;
+    }
+  }
+  double acc[4][8][2];
+#pragma unroll
+  for (int m = 0; m < 4; ++m)
+#pragma unroll
+    for (int nb = 0; nb < 8; ++nb) acc[m][nb][0] = acc[m][nb][1] = 0.0;
+
+  // ---- producer roles: warp w owns samples w, w+8, ..., lane = pixel within the chunk -------
+  double q_acc[8], dprod[8], ld_acc[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) { q_acc[e] = 0.0; dprod[e] = 1.0; ld_acc[e] = 0.0; }
+
+  auto produce = [&](int chunk, int buf) {
+    double* Ws = s_main + buf * STAGE_DOUBLES;
+    double* Gs = Ws + LK_TS * LK_WSTRIDE;
+    double* Ms = Gs + LK_TS * LK_WSTRIDE;
+    const int p = chunk * LK_KC + lane;
+    const bool pv = p < n;
+    double yp = 0, mup = 0, omp = 0, vp = 1;
+    if (pv) { yp = sp.y[p]; mup = sp.mu[p]; omp = sp.omega2[p]; vp = sp.v[p]; }
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      const int s = warp + 8 * e;
+      double w = 0.0, g = 0.0;
+      if (pv && tile_s0 + s < sp.num_samples) {
+        // absorption = product of the factors' profiles, left to right (dla_gp.py:370-386)
+        double a = sp.cache[(size_t)s_rows[s] * sp.ld + p];
+        for (int r = 1; r < sp.num_rows; ++r) a = a * sp.cache[(size_t)s_rows[r * LK_TS + s] * sp.ld + p];
+        const double a2 = a * a;
+        const double d = fma(omp, a2, vp);   // dla_omega2 + v
+        const double inv = 1.0 / d;
+        const double r = fma(-mup, a, yp);   // y - dla_mu
+        w = a2 * inv;
+        g = a * r * inv;
+        q_acc[e] = fma(r * r, inv, q_acc[e]);
+        dprod[e] *= d;
+      }
+      Ws[s * LK_WSTRIDE + lane] = w;
+      Gs[s * LK_WSTRIDE + lane] = g;
+    }
+    // fold the running product of d into the log-determinant every 8 chunks (range safety)
+    if ((chunk & 7) == 7) {
+#pragma unroll
+      for (int e = 0; e < 8; ++e) { ld_acc[e] += log(dprod[e]); dprod[e] = 1.0; }
+    }
+    // stage the M tile (rows beyond n are zero)
+    for (int e = tid; e < LK_KC * LK_K; e += LK_THREADS) {
+      const int pp = chunk * LK_KC + e / LK_K;
+      Ms[e] = pp < n ? sp.M[(size_t)chunk * LK_KC * LK_K + e] : 0.0;
+    }
+  };
+
+  auto consume = [&](int buf) {
+    const double* Ws = s_main + buf * STAGE_DOUBLES;
+    const double* Gs = Ws + LK_TS * LK_WSTRIDE;
+    const double* Ms = Gs + LK_TS * LK_WSTRIDE;
+    const int arow = (mhalf * 32 + grp) * LK_WSTRIDE + tig;
+#pragma unroll
+    for (int kb = 0; kb < LK_KC / 4; ++kb) {
+      double aw[4], ag[4];
+#pragma unroll
+      for (int m = 0; m < 4; ++m) aw[m] = Ws[arow + m * 8 * LK_WSTRIDE + kb * 4];
+      if (quarter == 3) {
+#pragma unroll
+        for (int m = 0; m < 4; ++m) ag[m] = Gs[arow + m * 8 * LK_WSTRIDE + kb * 4];
+      }
+      const double* mrow = Ms + (kb * 4 + tig) * LK_MSTRIDE;
+#pragma unroll
+      for (int nb = 0; nb < 8; ++nb) {
+        if (quarter == 3 && nb >= 6) continue;  // only 30 column blocks exist
+        if (quarter == 3 && nb >= 3) {
+          const double b = mrow[col_j[nb]];
+#pragma unroll
+          for (int m = 0; m < 4; ++m) dmma884(acc[m][nb][0], acc[m][nb][1], ag[m], b);
+        } else {
+          const double b = mrow[col_i[nb]] * mrow[col_j[nb]];
+#pragma unroll
+          for (int m = 0; m < 4; ++m) dmma884(acc[m][nb][0], acc[m][nb][1], aw[m], b);
+        }
+      }
+    }
+  };
+
+  // ---- main loop over pixel chunks, two stages ---------------------------------------------
+  produce(0, 0);
+  __syncthreads();
+  for (int chunk = 0; chunk < nchunks; ++chunk) {
+    const int buf = chunk & 1;
+    if (chunk + 1 < nchunks) produce(chunk + 1, buf ^ 1);
+    consume(buf);
+    __syncthreads();
+  }
+
+  // ---- per-sample scalar sums: reduce over the 32 pixel lanes -----------------------------
+#pragma unroll
+  for (int e = 0; e < 8; ++e) {
+    double q = q_acc[e];
+    double l = ld_acc[e] + log(dprod[e]);
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+      q += __shfl_xor_sync(0xffffffffu, q, off);
+      l += __shfl_xor_sync(0xffffffffu, l, off);
+    }
+    if (lane == 0) { s_sums[(warp + 8 * e) * 2] = q; s_sums[(warp + 8 * e) * 2 + 1] = l; }
+  }
+
+  // ---- accumulators -> E[col][sample] (overlays the stage buffers; all reads finished) -----
+  double* E = s_main;
+#pragma unroll
+  for (int m = 0; m < 4; ++m) {
+    const int s = mhalf * 32 + m * 8 + grp;
+#pragma unroll
+    for (int nb = 0; nb < 8; ++nb) {
+      const int blk = quarter * 8 + nb;
+      if (blk < LK_NBLK) {
+        const int col = blk * 8 + tig * 2;
+        E[col * LK_EP_STRIDE + s] = acc[m][nb][0];
+        E[(col + 1) * LK_EP_STRIDE + s] = acc[m][nb][1];
+      }
+    }
+  }
+  __syncthreads();
+
+  // ---- Cholesky of the bordered matrix [[B, c], [c', q]] : 4 threads per sample ------------
+  // E col layout: pair (i,j) at i(i+1)/2 + j ; projection c_j at 216 + j.
+  // Row 20 of the bordered factor is z = L^-1 c, so quad = q - z'z (null_gp.py:345-358).
+  {
+    const int s = tid >> 2;       // sample of this thread quad
+    const int t = tid & 3;
+    double* Es = E + s;
+    auto at = [&](int i, int j) -> double& {  // element (i,j), i >= j, i <= 20
+      const int col = (i < LK_K) ? (i * (i + 1) / 2 + j) : (216 + j);
+      return Es[col * LK_EP_STRIDE];
+    };
+    double logdet_prod = 1.0, logdet = 0.0, zz = 0.0;
+    for (int j = 0; j < LK_K; ++j) {
+      // pivot (all four threads compute it redundantly)
+      double piv = at(j, j) + 1.0;  // + I (null_gp.py:341)
+      for (int k = 0; k < j; ++k) { const double l = at(j, k); piv = fma(-l, l, piv); }
+      logdet_prod *= piv;
+      if ((j % 5) == 4) { logdet += log(logdet_prod); logdet_prod = 1.0; }
+      const double ljj = sqrt(piv);
+      const double inv = 1.0 / ljj;
+      __syncwarp();  // everyone has read row j before the diagonal is overwritten
+      // rows j+1 .. 20 of column j, interleaved over the quad
+      for (int i = j + 1 + t; i <= LK_K; i += 4) {
+        double x = at(i, j);
+        for (int k = 0; k < j; ++k) x = fma(-at(i, k), at(j, k), x);
+        x *= inv;
+        at(i, j) = x;
+        if (i == LK_K) zz = fma(x, x, zz);
+      }
+      __syncwarp();
+    }
+    // the thread that owned row 20 in column j is t == (20 - j - 1) & 3; sum the partial z'z
+    zz += __shfl_xor_sync(0xffffffffu, zz, 1);
+    zz += __shfl_xor_sync(0xffffffffu, zz, 2);
+    if (t == 0 && tile_s0 + s < sp.num_samples) {
+      const double quad = s_sums[s * 2] - zz;
+      const double log_det = s_sums[s * 2 + 1] + logdet;  // sum log d + 2 sum log L_ii
+      sp.out[tile_s0 + s] = -0.5 * (quad + log_det + (double)n * LK_LOG_2PI);
+    }
+  }
+}
+
+// -------------------------------------------------------------------------------------------
+// Generic single evaluation, any k <= 64: NullGP.log_mvnpdf_low_rank (null_gp.py:307-360)
+// called with explicit arrays.  One CTA; used by the staticmethod drop-in and the KATs.
+// -------------------------------------------------------------------------------------------
+constexpr int LG_MAXK = 64;
+__global__ void __launch_bounds__(256)
+log_mvnpdf_low_rank_kernel(const double* __restrict__ y, const double* __restrict__ mu, const double* __restrict__ M,
+                           const double* __restrict__ d, int n, int k, double* out) {
+  __shared__ double B[(LG_MAXK + 1) * (LG_MAXK + 1)];  // bordered (k+1) x (k+1), row-major, lower part used
+  __shared__ double red[2][8];
+  const int tid = threadIdx.x;
+  const int kb = k + 1;
+  // B[i][j] = sum_p M[p][i] M[p][j] / d[p]  (i >= j) ; B[k][j] = sum_p M[p][j] r[p] / d[p]
+  for (int e = tid; e < kb * kb; e += blockDim.x) {
+    const int i = e / kb, j = e % kb;
+    double acc = 0.0;
+    if (j <= i && j < k) {
+      for (int p = 0; p < n; ++p) {
+        const double left = (i < k) ? M[(size_t)p * k + i] : (y[p] - mu[p]);
+        acc = fma(left / d[p], M[(size_t)p * k + j], acc);
+      }
+      if (i == j) acc += 1.0;
+    }
+    B[e] = acc;
+  }
+  // scalar sums
+  double q = 0.0, ld = 0.0;
+  for (int p = tid; p < n; p += blockDim.x) {
+    const double r = y[p] - mu[p];
+    q = fma(r / d[p], r, q);
+    ld += log(d[p]);
+  }
+  for (int off = 16; off > 0; off >>= 1) {
+    q += __shfl_xor_sync(0xffffffffu, q, off);
+    ld += __shfl_xor_sync(0xffffffffu, ld, off);
+  }
+  if ((tid & 31) == 0) { red[0][tid >> 5] = q; red[1][tid >> 5] = ld; }
+  __syncthreads();
+  if (tid == 0) {
+    q = 0.0; ld = 0.0;
+    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) { q += red[0][w]; ld += red[1][w]; }
+    double logdet = 0.0, zz = 0.0;
+    for (int j = 0; j < k; ++j) {
+      double piv = B[j * kb + j];
+      for (int c = 0; c < j; ++c) piv = fma(-B[j * kb + c], B[j * kb + c], piv);
+      const double ljj = sqrt(piv);
+      logdet += log(ljj);
+      for (int i = j + 1; i <= k; ++i) {
+        double x = B[i * kb + j];
+        for (int c = 0; c < j; ++c) x = fma(-B[i * kb + c], B[j * kb + c], x);
+        x /= ljj;
+        B[i * kb + j] = x;
+        if (i == k) zz = fma(x, x, zz);
+      }
+    }
+    out[0] = -0.5 * ((q - zz) + (ld + 2.0 * logdet) + (double)n * LK_LOG_2PI);
+  }
+}
+
+}  // namespace dla

@@ -1,0 +1,248 @@
+"""
+synthetic.py : seeded synthetic inputs of the published shapes.
+
+The reference's learned model (`learned_qso_model_*.mat`), its QMC sample files
+(`dla_samples_a03.mat`, `subdla_samples.mat`), its prior catalogue (`catalog.mat`) and the
+SDSS FITS spectra are not available offline, so every test, the smoke run and `bench.py`
+draw their inputs from here.  Shapes follow the reference:
+
+* learned model : rest grid 911.75:0.25:1215.75 (1217 points), `mu`, `M` (1217 x 20),
+  `log_omega`, `log_c_0`, `log_tau_0`, `log_beta`            (null_gp.py:390-422)
+* DLA samples   : `offset_samples`, `log_nhi_samples`, `nhi_samples`  (dla_samples.py:67-77;
+  generate_dla_samples.m:8-57 - Halton sequence + inverse-CDF of the log N_HI mixture)
+* subDLA samples: log N_HI ~ U(19.5, 20) on the same offsets, `Z_lls`, `Z_dla`
+  (subdla_samples.py:82-125; multi_dlas/set_lls_parameters.m:58-71)
+* prior         : duck-typed `less_ind(z_qso)`                (model_priors.py:142-157)
+* spectra       : BOSS-like log-lambda grid, (wavelengths, flux, noise_variance, pixel_mask)
+  as `read_spec.read_spec` returns them                      (read_spec.py:22-71)
+
+This module is data synthesis only (host NumPy); it is not on the measured path.
+"""
+from typing import Dict, Tuple
+
+import numpy as np
+from scipy.special import wofz
+
+from .set_parameters import Parameters
+from . import _tables as tables
+
+
+# ----------------------------------------------------------------------------------------
+# learned GP model
+# ----------------------------------------------------------------------------------------
+def make_learned_model(seed: int = 0, k: int = 20) -> Dict[str, np.ndarray]:
+    """Synthetic stand-in for the learned null-model file."""
+    rng = np.random.default_rng(seed)
+    rest_wavelengths = 911.75 + 0.25 * np.arange(1217)
+
+    def bump(center, width, height):
+        return height * np.exp(-0.5 * ((rest_wavelengths - center) / width) ** 2)
+
+    mu = (
+        1.0
+        + 0.15 * (rest_wavelengths - 911.75) / 304.0
+        + bump(1215.67, 9.0, 1.9)
+        + bump(1025.72, 5.0, 0.35)
+        + bump(1033.8, 4.0, 0.25)
+        + bump(977.0, 3.0, 0.12)
+    )
+
+    # Gaussian-smoothed white noise columns, decaying scale
+    N = rest_wavelengths.shape[0]
+    kern_x = np.arange(-80, 81)
+    kern = np.exp(-0.5 * (kern_x / 20.0) ** 2)
+    kern /= np.sqrt(np.sum(kern**2))
+    M = np.empty((N, k))
+    for j in range(k):
+        white = rng.standard_normal(N + kern_x.shape[0] - 1)
+        M[:, j] = np.convolve(white, kern, "valid") * 0.2 * (0.85**j)
+
+    t = (rest_wavelengths - 911.75) / 304.0
+    log_omega = np.log(0.03 + 0.27 * (0.5 + 0.5 * np.cos(2.2 * np.pi * t + 0.3)) * (1 - 0.5 * t))
+
+    return dict(
+        rest_wavelengths=rest_wavelengths,
+        mu=mu,
+        M=np.ascontiguousarray(M),
+        log_omega=log_omega,
+        log_c_0=float(np.log(0.1)),
+        log_tau_0=float(np.log(0.0023)),
+        log_beta=float(np.log(3.65)),
+    )
+
+
+# ----------------------------------------------------------------------------------------
+# QMC samples
+# ----------------------------------------------------------------------------------------
+def halton(n: int, base: int, skip: int = 1) -> np.ndarray:
+    """First n points (after `skip`) of the van der Corput sequence in `base`."""
+    out = np.zeros(n)
+    idx = np.arange(skip, skip + n, dtype=np.int64)
+    f = 1.0
+    i = idx.copy()
+    while np.any(i > 0):
+        f = f / base
+        out += f * (i % base)
+        i //= base
+    return out
+
+
+def _mixture_inverse_cdf(u: np.ndarray, params: Parameters) -> np.ndarray:
+    """Inverse CDF of the log N_HI mixture prior of dla_samples.py:106-125."""
+    grid = np.linspace(params.fit_min_log_nhi, 25.0, 200001)
+    unnorm = np.exp(-1.2695 * grid**2 + 50.863 * grid - 509.33)
+    Z = np.trapezoid(unnorm, grid)
+    uni = ((grid >= params.uniform_min_log_nhi) & (grid <= params.uniform_max_log_nhi)) / (
+        params.uniform_max_log_nhi - params.uniform_min_log_nhi
+    )
+    pdf = params.alpha * unnorm / Z + (1 - params.alpha) * uni
+    cdf = np.concatenate([[0.0], np.cumsum(0.5 * (pdf[1:] + pdf[:-1]) * np.diff(grid))])
+    cdf /= cdf[-1]
+    return np.interp(u, cdf, grid)
+
+
+def make_dla_sample_arrays(params: Parameters, num_samples: int = None) -> Dict[str, np.ndarray]:
+    S = params.num_dla_samples if num_samples is None else num_samples
+    offset = halton(S, 2)
+    log_nhi = _mixture_inverse_cdf(halton(S, 3), params)
+    return dict(offset_samples=offset, log_nhi_samples=log_nhi, nhi_samples=10.0**log_nhi)
+
+
+def make_subdla_sample_arrays(params: Parameters, num_samples: int = None) -> Dict[str, np.ndarray]:
+    S = params.num_dla_samples if num_samples is None else num_samples
+    offset = halton(S, 2)
+    lo, hi = 19.5, 20.0
+    log_nhi = lo + (hi - lo) * halton(S, 3)
+    # partition functions (multi_dlas/set_lls_parameters.m:58-71): the DLA prior's peak value is
+    # extrapolated uniformly down to `lo`
+    grid = np.linspace(params.fit_min_log_nhi, 25.0, 200001)
+    unnorm = np.exp(-1.2695 * grid**2 + 50.863 * grid - 509.33)
+    Z_dla = float(np.trapezoid(unnorm, grid))
+    Z_lls = float(unnorm[0] * (hi - lo))
+    return dict(
+        offset_samples=offset,
+        log_nhi_samples=log_nhi,
+        nhi_samples=10.0**log_nhi,
+        Z_dla=Z_dla,
+        Z_lls=Z_lls,
+        extrapolate_min_log_nhi=lo,
+    )
+
+
+class SyntheticPrior:
+    """
+    Duck-typed stand-in for model_priors.PriorCatalog (only `less_ind` is on the path,
+    model_priors.py:142-157): a synthetic (z_qsos, dla_ind) catalogue with p(DLA) ~ 0.1.
+    """
+
+    def __init__(self, params: Parameters, num_quasars: int = 50000, seed: int = 1):
+        rng = np.random.default_rng(seed)
+        self.params = params
+        self.z_qsos = np.sort(2.15 + rng.gamma(2.0, 0.3, size=num_quasars))
+        p = 0.04 + 0.05 * (self.z_qsos - 2.15)
+        self.dla_ind = rng.random(num_quasars) < np.clip(p, 0.0, 0.4)
+
+    def less_ind(self, z_qso: float) -> Tuple[float, float]:
+        less_ind = self.z_qsos < (z_qso + self.params.prior_z_qso_increase)
+        return np.sum(self.dla_ind[less_ind]), np.sum(less_ind)
+
+
+# ----------------------------------------------------------------------------------------
+# spectra
+# ----------------------------------------------------------------------------------------
+def _host_voigt_absorption(wavelengths, nhi, z_dla, num_lines=3):
+    """scipy-based unbroadened absorption profile, for data synthesis only."""
+    c = tables.SPEED_OF_LIGHT_CGS
+    tot = np.zeros_like(wavelengths)
+    for l in range(num_lines):
+        vel = wavelengths * (c / (tables.TRANSITION_WAVELENGTHS[l] * (1 + z_dla)) / 1e8) - c
+        zz = (vel + 1j * tables.GAMMAS[l]) / (np.sqrt(2) * tables.SIGMA)
+        tot += -tables.LEADING_CONSTANTS[l] * np.real(wofz(zz)) / (np.sqrt(2 * np.pi) * tables.SIGMA)
+    return np.exp(nhi * tot)
+
+
+def sample_z_qsos(num: int, seed: int = 12345) -> np.ndarray:
+    """DR12Q-like quasar redshift distribution: 2.15 + Gamma tail, clipped at 5."""
+    rng = np.random.default_rng(seed)
+    return np.minimum(2.15 + rng.gamma(2.0, 0.25, size=num), 5.0)
+
+
+def make_spectrum(
+    model: Dict[str, np.ndarray],
+    z_qso: float,
+    seed: int,
+    num_pixels: int = 4650,
+    params: Parameters = None,
+) -> Tuple[np.ndarray, np.ndarray, np.ndarray, np.ndarray]:
+    """
+    One BOSS-like spectrum: (wavelengths, flux, noise_variance, pixel_mask) with the
+    meaning of read_spec.read_spec's return values (read_spec.py:22-71).
+    """
+    if params is None:
+        params = Parameters()
+    rng = np.random.default_rng(seed)
+
+    loglam = 3.5523 + 1e-4 * np.arange(num_pixels)
+    wavelengths = 10.0**loglam
+    rest = wavelengths / (1 + z_qso)
+
+    # continuum from the model inside its range; flat outside
+    rw = model["rest_wavelengths"]
+    inside = (rest >= rw[0]) & (rest <= rw[-1])
+    cont = np.ones(num_pixels)
+    cont[inside] = np.interp(rest[inside], rw, model["mu"])
+    cont[rest < rw[0]] = 0.3
+    cont[rest > rw[-1]] = np.interp(rw[-1], rw, model["mu"]) * np.exp(-(rest[rest > rw[-1]] - rw[-1]) / 40.0) + 1.0
+
+    # GP draw on the modelled range
+    xi = rng.standard_normal(model["M"].shape[1])
+    gp_draw = np.zeros(num_pixels)
+    for j in range(model["M"].shape[1]):
+        gp_draw[inside] += np.interp(rest[inside], rw, model["M"][:, j]) * xi[j]
+
+    # mean-flux suppression bluewards of Lya (Kim et al. parameters)
+    lya = params.lya_wavelength
+    z_abs = wavelengths / lya - 1
+    tau_eff = 0.0023 * (1 + z_abs) ** 3.65
+    suppress = np.where(rest < lya, np.exp(-tau_eff), 1.0)
+
+    # injected DLAs
+    absorption = np.ones(num_pixels)
+    num_dlas = rng.choice([0, 0, 0, 1, 1, 2, 3])
+    z_lo = max(wavelengths[0] / lya - 1, (1 + z_qso) * params.lyman_limit / lya - 1) + 0.01
+    z_hi = z_qso - 0.02
+    dlas = []
+    for _ in range(num_dlas):
+        if z_hi <= z_lo:
+            break
+        zd = rng.uniform(z_lo, z_hi)
+        ln = rng.uniform(20.0, 22.5)
+        dlas.append((zd, ln))
+        absorption *= _host_voigt_absorption(wavelengths, 10.0**ln, zd, 3)
+
+    omega = np.zeros(num_pixels)
+    omega[inside] = np.exp(np.interp(rest[inside], rw, model["log_omega"]))
+    forest_noise = omega * rng.standard_normal(num_pixels) * (1 - np.exp(-tau_eff) + 0.1) * (rest < lya)
+
+    clean = (cont + gp_draw + forest_noise) * suppress * absorption
+
+    sigma_pix = np.exp(rng.normal(np.log(0.25), 0.35, size=num_pixels)) * rng.uniform(0.5, 1.6)
+    noise_variance = sigma_pix**2
+    normaliser = np.exp(rng.normal(np.log(4.0), 0.6))
+
+    flux = (clean + sigma_pix * rng.standard_normal(num_pixels)) * normaliser
+    noise_variance = noise_variance * normaliser**2
+
+    # pixel mask: ivar == 0 (variance = inf, read_spec.py:59-63) or BRIGHTSKY (finite variance)
+    ivar0 = rng.random(num_pixels) < 0.012
+    bright = rng.random(num_pixels) < 0.004
+    # a short run of consecutive bad pixels now and then (sky-line residuals)
+    if rng.random() < 0.5:
+        start = rng.integers(0, num_pixels - 8)
+        ivar0[start : start + rng.integers(2, 8)] = True
+    with np.errstate(divide="ignore"):
+        noise_variance = np.where(ivar0, np.inf, noise_variance)
+    flux = np.where(ivar0, 0.0, flux)
+    pixel_mask = ivar0 | bright
+
+    return wavelengths, flux, noise_variance, pixel_mask
