@@ -74,6 +74,7 @@ SIGNATURES = {
     "dla_version": (c_char_p, []),
     "dla_last_kernel_ms": (c_double, []),
     "dla_kernel_launch_count": (c_longlong, []),
+    "dla_measure_fp64_peaks": (c_int, [_dp, _dp]),
     "dla_voigt_absorption": (c_int, [_dp, c_int, c_double, c_double, c_int, c_int, _dp]),
     "dla_voigt_absorption_batch": (c_int, [_dp, c_int, _dp, _dp, c_int, c_int, c_int, _dp]),
     "dla_faddeeva_re": (c_int, [_dp, _dp, c_int, _dp]),

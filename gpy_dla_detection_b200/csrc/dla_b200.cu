@@ -215,6 +215,70 @@ extern "C" double dla_last_kernel_ms(void) { return runtime().last_kernel_ms; }
 extern "C" long long dla_kernel_launch_count(void) { return runtime().launches; }
 
 // ------------------------------------------------------------------------------------------
+// FP64 peak probes (roofline denominators)
+// ------------------------------------------------------------------------------------------
+namespace dla {
+__global__ void __launch_bounds__(256) peak_dfma_kernel(double* out, double a, double b, int iters) {
+  double acc[16];
+#pragma unroll
+  for (int i = 0; i < 16; ++i) acc[i] = threadIdx.x * 1e-3 + i;
+  for (int it = 0; it < iters; ++it) {
+#pragma unroll
+    for (int i = 0; i < 16; ++i) acc[i] = fma(acc[i], a, b);
+  }
+  double s = 0;
+#pragma unroll
+  for (int i = 0; i < 16; ++i) s += acc[i];
+  if (s == 123.456) out[0] = s;
+}
+__global__ void __launch_bounds__(256) peak_dmma_kernel(double* out, double a, double b, int iters) {
+  double c0[8], c1[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) { c0[i] = i; c1[i] = -i; }
+  const double fa = a + threadIdx.x * 1e-9, fb = b;
+  for (int it = 0; it < iters; ++it) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) dmma884(c0[i], c1[i], fa, fb);
+  }
+  double s = 0;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) s += c0[i] + c1[i];
+  if (s == 123.456) out[0] = s;
+}
+}  // namespace dla
+
+extern "C" int dla_measure_fp64_peaks(double* dfma_tflops, double* dmma_tflops) {
+  DLA_CHECK_READY();
+  Runtime& rt = runtime();
+  DevBuf<double> sink;
+  DLA_CUDA(sink.alloc(1));
+  const int iters = 4096, blocks = rt.sm_count * 8, threads = 256;
+  cudaEvent_t e0, e1;
+  DLA_CUDA(cudaEventCreate(&e0));
+  DLA_CUDA(cudaEventCreate(&e1));
+  double best[2] = {1e30, 1e30};
+  for (int which = 0; which < 2; ++which) {
+    for (int rep = 0; rep < 8; ++rep) {
+      DLA_CUDA(cudaEventRecord(e0, rt.stream));
+      if (which == 0) peak_dfma_kernel<<<blocks, threads, 0, rt.stream>>>(sink.p, 1.0000001, 1e-9, iters);
+      else peak_dmma_kernel<<<blocks, threads, 0, rt.stream>>>(sink.p, 1.0000001, 1e-9, iters);
+      DLA_CUDA(cudaGetLastError());
+      DLA_CUDA(cudaEventRecord(e1, rt.stream));
+      DLA_CUDA(cudaEventSynchronize(e1));
+      float ms = 0.f;
+      DLA_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+      if (rep >= 2 && ms < best[which]) best[which] = ms;
+    }
+  }
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  const double nthreads = (double)blocks * threads;
+  if (dfma_tflops) *dfma_tflops = nthreads * iters * 16 * 2 / (best[0] * 1e-3) / 1e12;
+  if (dmma_tflops) *dmma_tflops = (nthreads / 32) * iters * 8 * 512.0 / (best[1] * 1e-3) / 1e12;
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------
 // a1: voigt
 // ------------------------------------------------------------------------------------------
 extern "C" int dla_voigt_absorption_batch(const double* wavelengths, int n_in, const double* nhis,

@@ -39,6 +39,11 @@ const char* dla_version(void);
 double dla_last_kernel_ms(void);
 long long dla_kernel_launch_count(void);  /* cumulative since dla_init */
 
+/* FP64 peaks of this device, measured now (about 0.3 s): DFMA vector pipe and DMMA m8n8k4
+ * tensor path, in TFLOP/s.  bench.py uses them as the roofline denominators because
+ * MEASURED_PEAKS.json carries no FP64 figure. */
+int dla_measure_fp64_peaks(double* dfma_tflops, double* dmma_tflops);
+
 /* ---- a1: voigt.voigt_absorption (voigt.py:251-322; voigt.c:253-304) ---------------- */
 /* out has n_in - 6 entries when broadening != 0, else n_in */
 int dla_voigt_absorption(const double* wavelengths, int n_in, double nhi, double z_dla,
