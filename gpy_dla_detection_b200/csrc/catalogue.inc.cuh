@@ -78,7 +78,7 @@ struct dla_catalogue {
   DevBuf<uint8_t> ind_unmasked, ind;
   DevBuf<double> x, y, v, this_wl, mu, omega2, M, unmasked_wl, wl_abs, padded_wl, scratch, scalars;
   DevBuf<int32_t> uidx;
-  DevBuf<double> z_samples, cache, raw_ll0, raw_ll, sample_ll_dla, sample_ll_sub, log_ev_dla, log_ev_sub, cdf;
+  DevBuf<double> z_samples, cache, prod, raw_ll0, raw_ll, sample_ll_dla, sample_ll_sub, log_ev_dla, log_ev_sub, cdf;
   DevBuf<double> log_lik, log_priors, log_post, model_post, p_dla, p_no_dla, map_z, map_lognhi;
   DevBuf<int32_t> rows, inds_t, map_ind;
   DevBuf<int> alive;  // [B][4] : DLA level-loop alive flag, status, usable (constant), pad
@@ -302,8 +302,8 @@ extern "C" int dla_catalogue_run_staged(dla_catalogue* cat, dla_catalogue_output
 
     // ---- 2. sizes, cache layout, descriptors ---------------------------------------------------
     std::vector<int> n_b(nb), nu_b(nb), ld_b(nb);
-    std::vector<size_t> cache_off(nb);
-    size_t cache_total = 0;
+    std::vector<size_t> cache_off(nb), prod_off(nb);
+    size_t cache_total = 0, prod_total = 0;
     int max_n_abs = 1;
     for (int b = 0; b < nb; ++b) {
       nu_b[b] = (int)h_scalars[(size_t)b * 8 + 0];
@@ -311,9 +311,12 @@ extern "C" int dla_catalogue_run_staged(dla_catalogue* cat, dla_catalogue_output
       ld_b[b] = (int)round_up(std::max(n_b[b], 1), 4);
       cache_off[b] = cache_total;
       cache_total += (size_t)(2 * S + 1) * ld_b[b];
+      prod_off[b] = prod_total;
+      if (md >= 3) prod_total += (size_t)S * ld_b[b];
       max_n_abs = std::max(max_n_abs, cat->params.broadening ? nu_b[b] + 2 * w : nu_b[b]);
     }
     DLA_CUDA(cat->cache.ensure(cache_total));
+    DLA_CUDA(cat->prod.ensure(prod_total));
 
     h_grid.resize(nb);
     h_lk.assign((size_t)nb * md, LikelihoodSpectrum());
@@ -346,21 +349,28 @@ extern "C" int dla_catalogue_run_staged(dla_catalogue* cat, dla_catalogue_output
         d.omega2 = h_prep[b].omega2;
         d.M = h_prep[b].M;
         d.cache = cache_b;
+        d.rows0 = nullptr;
         d.alive = cat->alive.p + (size_t)b * 4;
         d.n = n_b[b];
         d.ld = ld_b[b];
         d.row0 = 0;
         if (level == 0) {  // DLA + subDLA + null rows in one go
+          d.base0 = cache_b;
           d.rows = nullptr;
+          d.prod_out = nullptr;
           d.out = cat->raw_ll0.p + (size_t)b * (2 * S + 1);
           d.num_samples = 2 * S + 1;
           d.num_rows = 1;
           d.row_stride = 0;
         } else {
-          d.rows = cat->rows.p + (size_t)b * S * md;
+          // running product of the previous level (row s) x profile of the newly drawn absorber
+          double* prod_b = cat->prod.p + prod_off[b];
+          d.base0 = level == 1 ? cache_b : prod_b;
+          d.rows = cat->rows.p + (size_t)b * S * md + (size_t)level * S;
+          d.prod_out = (level + 1 < md) ? prod_b : nullptr;
           d.out = cat->raw_ll.p + (size_t)b * S;
           d.num_samples = S;
-          d.num_rows = level + 1;
+          d.num_rows = 2;
           d.row_stride = S;
         }
         h_lk[(size_t)level * nb + b] = d;

@@ -155,7 +155,7 @@ struct dla_spectrum {
   DevBuf<double> x, y, v, this_wl, mu, omega2, M, unmasked_wl, wl_abs, padded_wl, d_scalars;
   DevBuf<int32_t> uidx;
   // work buffers (grown on demand)
-  DevBuf<double> cache, z_dev, nhi_dev, uniforms, raw_ll, sample_ll, log_ev, cdf;
+  DevBuf<double> cache, prod, z_dev, nhi_dev, uniforms, raw_ll, sample_ll, log_ev, cdf;
   DevBuf<int32_t> rows;
   DevBuf<int> alive;
   DevBuf<LikelihoodSpectrum> lk_desc;
@@ -619,8 +619,11 @@ static LikelihoodSpectrum base_desc(dla_spectrum* sp) {
   d.mu = sp->mu.p;
   d.omega2 = sp->omega2.p;
   d.M = sp->M.p;
+  d.base0 = sp->cache.p;
   d.cache = sp->cache.p;
+  d.rows0 = nullptr;
   d.rows = nullptr;
+  d.prod_out = nullptr;
   d.out = nullptr;
   d.n = sp->n;
   d.ld = sp->ld;
@@ -654,6 +657,7 @@ extern "C" int dla_null_log_model_evidence(dla_spectrum* sp, double* out) {
   fill_double_kernel<<<(sp->ld + 255) / 256, 256, 0, rt.stream>>>(ones.p, sp->ld, 1.0);
   DLA_LAUNCHED();
   LikelihoodSpectrum d = base_desc(sp);
+  d.base0 = ones.p;
   d.cache = ones.p;
   d.out = res.p;
   d.num_samples = 1;
@@ -757,6 +761,7 @@ extern "C" int dla_log_model_evidences(dla_spectrum* sp, const double* z_samples
   }
   int rc = ensure_cache(sp, S);
   if (rc) return rc;
+  if (max_dlas >= 3) DLA_CUDA(sp->prod.ensure((size_t)S * sp->ld));
   DLA_CUDA(sp->raw_ll.ensure(S));
   DLA_CUDA(sp->sample_ll.ensure((size_t)S * max_dlas));
   DLA_CUDA(sp->log_ev.ensure(max_dlas));
@@ -773,9 +778,13 @@ extern "C" int dla_log_model_evidences(dla_spectrum* sp, const double* z_samples
     LikelihoodSpectrum d = base_desc(sp);
     d.out = sp->raw_ll.p;
     d.num_samples = S;
-    d.num_rows = level + 1;
-    d.rows = sp->rows.p;
+    // level L >= 1 multiplies the running product of level L-1 (row s of `prod`, or the sample's own
+    // profile at L == 1) by the profile of the newly drawn absorber base_sample_inds[L-1][s]
+    d.num_rows = level == 0 ? 1 : 2;
+    d.base0 = level <= 1 ? sp->cache.p : sp->prod.p;
+    d.rows = level == 0 ? nullptr : sp->rows.p + (size_t)level * S;
     d.row_stride = S;
+    d.prod_out = (level >= 1 && level + 1 < max_dlas) ? sp->prod.p : nullptr;
     d.alive = sp->alive.p;
     lk[level] = d;
     EvidenceLevel e;

@@ -39,25 +39,34 @@ __device__ __constant__ uint8_t c_pair_i[LK_NBLK_PAIR * 8];
 __device__ __constant__ uint8_t c_pair_j[LK_NBLK_PAIR * 8];
 
 // One spectrum as the likelihood kernel sees it.
+// Factor r of sample s is a row of a profile matrix:
+//   r == 0 : base0[ row(0,s) * ld ]   (profile cache, or the running-product buffer of the previous level)
+//   r >= 1 : cache[ row(r,s) * ld ]
+//   row(0,s) = rows0 ? rows0[s] : row0 + s
+//   row(r,s) = rows  ? rows[(r-1) * row_stride + s] : row0 + r * row_stride + s
+// The absorption is the left-to-right product of the factors (dla_gp.py:370-386).  When
+// prod_out is set the product is stored as row s of prod_out, so the next level of
+// DLAGP.log_model_evidences reads two rows per sample instead of level+1.
 struct LikelihoodSpectrum {
   const double* y;       // n   normalised flux of the modelled pixels
   const double* v;       // n   noise variance
   const double* mu;      // n   this_mu  (mean-flux suppressed)
   const double* omega2;  // n   this_omega2
   const double* M;       // n x 20 row-major this_M
-  const double* cache;   // profile rows, stride ld
-  const int32_t* rows;   // [num_rows][row_stride] profile-row index of each factor, or nullptr:
-                         //   factor r of sample s is profile row row0 + r * row_stride + s
+  const double* base0;   // profile rows of factor 0, stride ld
+  const double* cache;   // profile rows of factors >= 1, stride ld
+  const int32_t* rows0;  // factor-0 row per sample, or nullptr
+  const int32_t* rows;   // factor >= 1 rows, or nullptr
   const int* alive;      // if non-null and *alive == 0 the spectrum left the level loop (NaN evidence): skip
+  double* prod_out;      // optional: product rows out (may alias base0 rows of the same sample)
   double* out;           // num_samples raw log-likelihoods
   int n;                 // modelled pixels
   int ld;                // profile row stride
   int num_samples;       // samples in this launch
   int num_rows;          // factors per sample (1..LK_MAX_ROWS)
   int row_stride;        // stride between factor arrays in `rows`
-  int row0;              // first profile row when rows == nullptr
+  int row0;              // first profile row when the row arrays are null
 };
-
 
 __device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double b) {
   asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
@@ -65,10 +74,35 @@ __device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double
                : "d"(a), "d"(b));
 }
 
-constexpr size_t LK_TILE_BYTES = (2 * LK_TS * LK_WSTRIDE + LK_KC * LK_MSTRIDE) * sizeof(double);
-constexpr size_t LK_EP_BYTES = (size_t)LK_EP_COLS * LK_EP_STRIDE * sizeof(double);
+// cp.async (LDGSTS): global -> shared without a register round trip
+__device__ __forceinline__ void cp_async8(void* smem_dst, const void* gmem_src) {
+  const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"(d), "l"(gmem_src) : "memory");
+}
+__device__ __forceinline__ void cp_async16_zfill(void* smem_dst, const void* gmem_src, int src_bytes) {
+  const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 16, %2;\n" ::"r"(d), "l"(gmem_src), "r"(src_bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;\n" ::: "memory"); }
+
+// ---- shared memory plan ----------------------------------------------------------------------
+//   WG   : 2 stages x { W[64][36], G[64][36] }                       73 728 B
+//   MR   : 3-deep ring of M tiles [32][20]                            15 360 B
+//   STG  : thread-private staging slots filled by cp.async one chunk ahead:
+//          2 factor rows x 8 samples + y, mu, omega2, v  -> [20][256] 40 960 B
+//   E    : epilogue matrix [240][65], overlays WG + MR + STG         124 800 B
+//   AUX  : per-sample sums [64][2], profile rows [8][64]
+constexpr int LK_STG_ROWS = 2;                                   // factors staged by cp.async (others load directly)
+constexpr int LK_WG_DOUBLES = 2 * 2 * LK_TS * LK_WSTRIDE;        // 9216
+constexpr int LK_MR_DOUBLES = 3 * LK_KC * LK_MSTRIDE;            // 1920
+constexpr int LK_STG_SLOTS = LK_STG_ROWS * 8 + 4;                // 20
+constexpr int LK_STG_DOUBLES = LK_STG_SLOTS * LK_THREADS;        // 5120
+constexpr int LK_MAIN_DOUBLES_RAW = LK_WG_DOUBLES + LK_MR_DOUBLES + LK_STG_DOUBLES;
+constexpr int LK_EP_DOUBLES = LK_EP_COLS * LK_EP_STRIDE;
+constexpr int LK_MAIN_DOUBLES = LK_MAIN_DOUBLES_RAW > LK_EP_DOUBLES ? LK_MAIN_DOUBLES_RAW : LK_EP_DOUBLES;
 constexpr size_t LK_AUX_BYTES = LK_TS * 2 * sizeof(double) + LK_MAX_ROWS * LK_TS * sizeof(int32_t);
-constexpr size_t LK_SMEM_BYTES = (LK_EP_BYTES > 2 * LK_TILE_BYTES ? LK_EP_BYTES : 2 * LK_TILE_BYTES) + LK_AUX_BYTES;
+constexpr size_t LK_SMEM_BYTES = (size_t)LK_MAIN_DOUBLES * sizeof(double) + LK_AUX_BYTES;
 
 // grid = (ceil(max num_samples / 64), num_spectra), block = 256, dynamic smem = LK_SMEM_BYTES
 __global__ void __launch_bounds__(LK_THREADS, 1)
@@ -79,26 +113,28 @@ sample_likelihood_kernel(const LikelihoodSpectrum* __restrict__ specs) {
   if (tile_s0 >= sp.num_samples) return;
   if (sp.alive && *sp.alive == 0) return;
 
-  // ---- shared memory carve-up -----------------------------------------------------------
-  // main loop : 2 stages x { W[64][36], G[64][36], M[32][20] }
-  // epilogue  : E[240][65] overlays the stages
   double* s_main = reinterpret_cast<double*>(smem_raw);
-  const size_t main_doubles = (LK_EP_BYTES > 2 * LK_TILE_BYTES ? LK_EP_BYTES : 2 * LK_TILE_BYTES) / sizeof(double);
-  double* s_sums = s_main + main_doubles;                        // [64][2] : sum r^2/d, sum log d
-  int32_t* s_rows = reinterpret_cast<int32_t*>(s_sums + LK_TS * 2);  // [num_rows][64]
-  constexpr int STAGE_DOUBLES = 2 * LK_TS * LK_WSTRIDE + LK_KC * LK_MSTRIDE;
+  double* s_wg = s_main;
+  double* s_mr = s_wg + LK_WG_DOUBLES;
+  double* s_stg = s_mr + LK_MR_DOUBLES;
+  double* s_sums = s_main + LK_MAIN_DOUBLES;                          // [64][2] : sum r^2/d, sum log d
+  int32_t* s_rows = reinterpret_cast<int32_t*>(s_sums + LK_TS * 2);   // [num_rows][64]
 
   const int tid = threadIdx.x;
   const int warp = tid >> 5, lane = tid & 31;
   const int n = sp.n;
   const int nchunks = (n + LK_KC - 1) / LK_KC;
+  const int num_rows = sp.num_rows;
 
   // ---- profile rows of the tile's samples -----------------------------------------------
-  for (int e = tid; e < sp.num_rows * LK_TS; e += LK_THREADS) {
+  for (int e = tid; e < num_rows * LK_TS; e += LK_THREADS) {
     const int r = e / LK_TS, s = e % LK_TS;
     const int gs = tile_s0 + s;
     int row = 0;
-    if (gs < sp.num_samples) row = sp.rows ? sp.rows[(size_t)r * sp.row_stride + gs] : sp.row0 + r * sp.row_stride + gs;
+    if (gs < sp.num_samples) {
+      if (r == 0) row = sp.rows0 ? sp.rows0[gs] : sp.row0 + gs;
+      else row = sp.rows ? sp.rows[(size_t)(r - 1) * sp.row_stride + gs] : sp.row0 + r * sp.row_stride + gs;
+    }
     s_rows[r * LK_TS + s] = row;
   }
   __syncthreads();
@@ -132,23 +168,58 @@ sample_likelihood_kernel(const LikelihoodSpectrum* __restrict__ specs) {
   double q_acc[8], dprod[8], ld_acc[8];
 #pragma unroll
   for (int e = 0; e < 8; ++e) { q_acc[e] = 0.0; dprod[e] = 1.0; ld_acc[e] = 0.0; }
+  double* my_stg = s_stg + tid;  // slot k of this thread at my_stg[k * 256]
 
+  // issue the global->shared copies of one chunk: factor rows (first two), pixel scalars, M tile
+  auto prefetch = [&](int chunk) {
+    const int p = chunk * LK_KC + lane;
+    if (p < n) {
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        const int s = warp + 8 * e;
+        if (tile_s0 + s < sp.num_samples) {
+          cp_async8(my_stg + e * LK_THREADS, sp.base0 + (size_t)s_rows[s] * sp.ld + p);
+          if (num_rows > 1)
+            cp_async8(my_stg + (8 + e) * LK_THREADS, sp.cache + (size_t)s_rows[LK_TS + s] * sp.ld + p);
+        }
+      }
+      cp_async8(my_stg + 16 * LK_THREADS, sp.y + p);
+      cp_async8(my_stg + 17 * LK_THREADS, sp.mu + p);
+      cp_async8(my_stg + 18 * LK_THREADS, sp.omega2 + p);
+      cp_async8(my_stg + 19 * LK_THREADS, sp.v + p);
+    }
+    // M tile: 640 doubles = 320 x 16 B, zero-filled beyond pixel n
+    double* Mt = s_mr + (chunk % 3) * (LK_KC * LK_MSTRIDE);
+    for (int e2 = tid; e2 < LK_KC * LK_K / 2; e2 += LK_THREADS) {
+      const int pp = chunk * LK_KC + (2 * e2) / LK_K;
+      // clamp the source so the address is always valid; src_bytes = 0 zero-fills
+      const double* src = sp.M + (size_t)(pp < n ? (chunk * LK_KC * LK_K + 2 * e2) : 0);
+      cp_async16_zfill(Mt + 2 * e2, src, pp < n ? 16 : 0);
+    }
+    cp_async_commit();
+  };
+
+  // turn the staged values of one chunk into the W / G operand tiles
   auto produce = [&](int chunk, int buf) {
-    double* Ws = s_main + buf * STAGE_DOUBLES;
+    double* Ws = s_wg + buf * (2 * LK_TS * LK_WSTRIDE);
     double* Gs = Ws + LK_TS * LK_WSTRIDE;
-    double* Ms = Gs + LK_TS * LK_WSTRIDE;
     const int p = chunk * LK_KC + lane;
     const bool pv = p < n;
     double yp = 0, mup = 0, omp = 0, vp = 1;
-    if (pv) { yp = sp.y[p]; mup = sp.mu[p]; omp = sp.omega2[p]; vp = sp.v[p]; }
+    if (pv) {
+      yp = my_stg[16 * LK_THREADS]; mup = my_stg[17 * LK_THREADS];
+      omp = my_stg[18 * LK_THREADS]; vp = my_stg[19 * LK_THREADS];
+    }
 #pragma unroll
     for (int e = 0; e < 8; ++e) {
       const int s = warp + 8 * e;
       double w = 0.0, g = 0.0;
       if (pv && tile_s0 + s < sp.num_samples) {
         // absorption = product of the factors' profiles, left to right (dla_gp.py:370-386)
-        double a = sp.cache[(size_t)s_rows[s] * sp.ld + p];
-        for (int r = 1; r < sp.num_rows; ++r) a = a * sp.cache[(size_t)s_rows[r * LK_TS + s] * sp.ld + p];
+        double a = my_stg[e * LK_THREADS];
+        if (num_rows > 1) a = a * my_stg[(8 + e) * LK_THREADS];
+        for (int r = 2; r < num_rows; ++r) a = a * sp.cache[(size_t)s_rows[r * LK_TS + s] * sp.ld + p];
+        if (sp.prod_out) sp.prod_out[(size_t)(tile_s0 + s) * sp.ld + p] = a;
         const double a2 = a * a;
         const double d = fma(omp, a2, vp);   // dla_omega2 + v
         const double inv = 1.0 / d;
@@ -166,17 +237,12 @@ sample_likelihood_kernel(const LikelihoodSpectrum* __restrict__ specs) {
 #pragma unroll
       for (int e = 0; e < 8; ++e) { ld_acc[e] += log(dprod[e]); dprod[e] = 1.0; }
     }
-    // stage the M tile (rows beyond n are zero)
-    for (int e = tid; e < LK_KC * LK_K; e += LK_THREADS) {
-      const int pp = chunk * LK_KC + e / LK_K;
-      Ms[e] = pp < n ? sp.M[(size_t)chunk * LK_KC * LK_K + e] : 0.0;
-    }
   };
 
-  auto consume = [&](int buf) {
-    const double* Ws = s_main + buf * STAGE_DOUBLES;
+  auto consume = [&](int chunk, int buf) {
+    const double* Ws = s_wg + buf * (2 * LK_TS * LK_WSTRIDE);
     const double* Gs = Ws + LK_TS * LK_WSTRIDE;
-    const double* Ms = Gs + LK_TS * LK_WSTRIDE;
+    const double* Ms = s_mr + (chunk % 3) * (LK_KC * LK_MSTRIDE);
     const int arow = (mhalf * 32 + grp) * LK_WSTRIDE + tig;
 #pragma unroll
     for (int kb = 0; kb < LK_KC / 4; ++kb) {
@@ -204,16 +270,22 @@ sample_likelihood_kernel(const LikelihoodSpectrum* __restrict__ specs) {
     }
   };
 
-  // ---- main loop over pixel chunks, two stages ---------------------------------------------
-  produce(0, 0);
-  __syncthreads();
+  // ---- main loop: chunk c+2 in flight (cp.async), chunk c+1 being produced, chunk c in the MMAs ----
+  prefetch(0);
+  cp_async_wait_all();
+  produce(0, 0);          // reads only this thread's own staging slots
+  if (nchunks > 1) prefetch(1);
+  __syncthreads();        // W/G(0) and M(0) visible to all warps
   for (int chunk = 0; chunk < nchunks; ++chunk) {
     const int buf = chunk & 1;
-    if (chunk + 1 < nchunks) produce(chunk + 1, buf ^ 1);
-    consume(buf);
+    if (chunk + 1 < nchunks) {
+      cp_async_wait_all();             // staged values + M tile of chunk+1 have landed (issued one MMA phase ago)
+      produce(chunk + 1, buf ^ 1);
+      if (chunk + 2 < nchunks) prefetch(chunk + 2);
+    }
+    consume(chunk, buf);
     __syncthreads();
   }
-
   // ---- per-sample scalar sums: reduce over the 32 pixel lanes -----------------------------
 #pragma unroll
   for (int e = 0; e < 8; ++e) {
