@@ -17,12 +17,13 @@
 // fragments.  HBM sees only the profile rows (read) and one double per sample (written).
 #pragma once
 #include <stdint.h>
+#include <type_traits>
 
 namespace dla {
 
 constexpr int LK_K = 20;                        // rank of the learned covariance (Parameters.k)
 constexpr int LK_PAIRS = LK_K * (LK_K + 1) / 2;  // 210 lower-triangle pairs
-constexpr int LK_TS = 64;                        // samples per CTA tile
+constexpr int LK_TS = 32;                        // samples per CTA tile (two CTAs share an SM)
 constexpr int LK_KC = 32;                        // pixels per chunk
 constexpr int LK_WSTRIDE = LK_KC + 4;            // padded row stride of the W/G tiles (conflict-free DMMA A loads)
 constexpr int LK_MSTRIDE = LK_K;                 // row stride of the M tile (20 == 4 mod 16: conflict-free B loads)
@@ -30,7 +31,7 @@ constexpr int LK_THREADS = 256;
 constexpr int LK_NBLK_PAIR = 27;                 // ceil(210 / 8) column blocks of the Gram part
 constexpr int LK_NBLK = 30;                      // + 3 column blocks (24 >= 20) of the projection part
 constexpr int LK_EP_COLS = 216 + 24;             // columns staged for the epilogue
-constexpr int LK_EP_STRIDE = LK_TS + 1;          // epilogue smem: [col][sample], stride 65
+constexpr int LK_EP_STRIDE = LK_TS + 1;          // epilogue smem: [col][sample], stride 33
 constexpr int LK_MAX_ROWS = 8;                   // max absorbers multiplied per sample (max_dlas <= 8)
 constexpr double LK_LOG_2PI = 1.83787706640934534;  // null_gp.py:325
 
@@ -86,26 +87,30 @@ __device__ __forceinline__ void cp_async16_zfill(void* smem_dst, const void* gme
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;\n" ::: "memory"); }
 
-// ---- shared memory plan ----------------------------------------------------------------------
-//   WG   : 2 stages x { W[64][36], G[64][36] }                       73 728 B
+// ---- shared memory plan (per CTA; two CTAs are resident per SM) -----------------------------------
+//   WG   : 2 stages x { W[32][36], G[32][36] }                       36 864 B
 //   MR   : 3-deep ring of M tiles [32][20]                            15 360 B
 //   STG  : thread-private staging slots filled by cp.async one chunk ahead:
-//          2 factor rows x 8 samples + y, mu, omega2, v  -> [20][256] 40 960 B
-//   E    : epilogue matrix [240][65], overlays WG + MR + STG         124 800 B
-//   AUX  : per-sample sums [64][2], profile rows [8][64]
+//          2 factor rows x 4 samples + y, mu, omega2, v  -> [12][256] 24 576 B
+//   E    : epilogue matrix [240][33], overlays WG + MR + STG          63 360 B
+//   AUX  : per-sample sums [32][2], profile rows [8][32]
 constexpr int LK_STG_ROWS = 2;                                   // factors staged by cp.async (others load directly)
-constexpr int LK_WG_DOUBLES = 2 * 2 * LK_TS * LK_WSTRIDE;        // 9216
+constexpr int LK_EPT = LK_TS * LK_KC / LK_THREADS;               // elements per thread per chunk (4)
+constexpr int LK_WG_DOUBLES = 2 * 2 * LK_TS * LK_WSTRIDE;        // 4608
 constexpr int LK_MR_DOUBLES = 3 * LK_KC * LK_MSTRIDE;            // 1920
-constexpr int LK_STG_SLOTS = LK_STG_ROWS * 8 + 4;                // 20
-constexpr int LK_STG_DOUBLES = LK_STG_SLOTS * LK_THREADS;        // 5120
+constexpr int LK_STG_SLOTS = LK_STG_ROWS * LK_EPT + 4;           // 12
+constexpr int LK_STG_DOUBLES = LK_STG_SLOTS * LK_THREADS;        // 3072
 constexpr int LK_MAIN_DOUBLES_RAW = LK_WG_DOUBLES + LK_MR_DOUBLES + LK_STG_DOUBLES;
 constexpr int LK_EP_DOUBLES = LK_EP_COLS * LK_EP_STRIDE;
 constexpr int LK_MAIN_DOUBLES = LK_MAIN_DOUBLES_RAW > LK_EP_DOUBLES ? LK_MAIN_DOUBLES_RAW : LK_EP_DOUBLES;
 constexpr size_t LK_AUX_BYTES = LK_TS * 2 * sizeof(double) + LK_MAX_ROWS * LK_TS * sizeof(int32_t);
 constexpr size_t LK_SMEM_BYTES = (size_t)LK_MAIN_DOUBLES * sizeof(double) + LK_AUX_BYTES;
+constexpr int LK_NWARPS = LK_THREADS / 32;                       // 8
+constexpr int LK_MB = LK_TS / 8;                                 // DMMA row blocks per warp tile (4)
+constexpr int LK_NB = 4;                                         // DMMA column blocks per warp (8 warps x 4 >= 30)
 
-// grid = (ceil(max num_samples / 64), num_spectra), block = 256, dynamic smem = LK_SMEM_BYTES
-__global__ void __launch_bounds__(LK_THREADS, 1)
+// grid = (ceil(max num_samples / 32), num_spectra), block = 256, dynamic smem = LK_SMEM_BYTES
+__global__ void __launch_bounds__(LK_THREADS, 2)
 sample_likelihood_kernel(const LikelihoodSpectrum* __restrict__ specs) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const LikelihoodSpectrum sp = specs[blockIdx.y];
@@ -117,8 +122,8 @@ sample_likelihood_kernel(const LikelihoodSpectrum* __restrict__ specs) {
   double* s_wg = s_main;
   double* s_mr = s_wg + LK_WG_DOUBLES;
   double* s_stg = s_mr + LK_MR_DOUBLES;
-  double* s_sums = s_main + LK_MAIN_DOUBLES;                          // [64][2] : sum r^2/d, sum log d
-  int32_t* s_rows = reinterpret_cast<int32_t*>(s_sums + LK_TS * 2);   // [num_rows][64]
+  double* s_sums = s_main + LK_MAIN_DOUBLES;                          // [32][2] : sum r^2/d, sum log d
+  int32_t* s_rows = reinterpret_cast<int32_t*>(s_sums + LK_TS * 2);   // [num_rows][32]
 
   const int tid = threadIdx.x;
   const int warp = tid >> 5, lane = tid & 31;
@@ -126,7 +131,7 @@ sample_likelihood_kernel(const LikelihoodSpectrum* __restrict__ specs) {
   const int nchunks = (n + LK_KC - 1) / LK_KC;
   const int num_rows = sp.num_rows;
 
-  // ---- profile rows of the tile's samples -----------------------------------------------
+  // ---- profile rows of the tile's samples, zeroed sums -----------------------------------
   for (int e = tid; e < num_rows * LK_TS; e += LK_THREADS) {
     const int r = e / LK_TS, s = e % LK_TS;
     const int gs = tile_s0 + s;
@@ -137,18 +142,17 @@ sample_likelihood_kernel(const LikelihoodSpectrum* __restrict__ specs) {
     }
     s_rows[r * LK_TS + s] = row;
   }
+  if (tid < LK_TS * 2) s_sums[tid] = 0.0;
   __syncthreads();
 
-  // ---- MMA roles: warp = (mhalf, quarter); warp tile = 32 samples x 8 column blocks --------
-  const int mhalf = warp >> 2;    // samples [32*mhalf, 32*mhalf+32)
-  const int quarter = warp & 3;   // column blocks [8*quarter, 8*quarter+8)  (quarter 3: 24..26 pairs + 3 projection)
+  // ---- MMA roles: warp w owns column blocks [4w, 4w+4) for all 32 samples -----------------
+  //      blocks 0..26 = Gram pairs (A = W), blocks 27..29 = projection (A = G), 30,31 do not exist
   const int grp = lane >> 2;      // DMMA groupID
   const int tig = lane & 3;       // DMMA threadID_in_group
-  // per-lane column operands: for block nb, this lane provides B[k=tig][n=grp]
-  int col_i[8], col_j[8];
+  int col_i[LK_NB], col_j[LK_NB];
 #pragma unroll
-  for (int nb = 0; nb < 8; ++nb) {
-    const int blk = quarter * 8 + nb;
+  for (int nb = 0; nb < LK_NB; ++nb) {
+    const int blk = warp * LK_NB + nb;
     if (blk < LK_NBLK_PAIR) {
       col_i[nb] = c_pair_i[blk * 8 + grp];
       col_j[nb] = c_pair_j[blk * 8 + grp];
@@ -158,35 +162,47 @@ sample_likelihood_kernel(const LikelihoodSpectrum* __restrict__ specs) {
       col_j[nb] = j < LK_K ? j : 0;
     }
   }
-  double acc[4][8][2];
+  double acc[LK_MB][LK_NB][2];
 #pragma unroll
-  for (int m = 0; m < 4; ++m)
+  for (int m = 0; m < LK_MB; ++m)
 #pragma unroll
-    for (int nb = 0; nb < 8; ++nb) acc[m][nb][0] = acc[m][nb][1] = 0.0;
+    for (int nb = 0; nb < LK_NB; ++nb) acc[m][nb][0] = acc[m][nb][1] = 0.0;
 
-  // ---- producer roles: warp w owns samples w, w+8, ..., lane = pixel within the chunk -------
-  double q_acc[8], dprod[8], ld_acc[8];
+  // ---- producer roles: warp w owns samples w, w+8, w+16, w+24; lane = pixel within the chunk ----
+  double q_acc[LK_EPT], dprod[LK_EPT];
 #pragma unroll
-  for (int e = 0; e < 8; ++e) { q_acc[e] = 0.0; dprod[e] = 1.0; ld_acc[e] = 0.0; }
+  for (int e = 0; e < LK_EPT; ++e) { q_acc[e] = 0.0; dprod[e] = 1.0; }
   double* my_stg = s_stg + tid;  // slot k of this thread at my_stg[k * 256]
+
+  // fold the running products of d into the per-sample log-determinant sums (only this warp touches its samples)
+  auto fold_logdet = [&]() {
+#pragma unroll
+    for (int e = 0; e < LK_EPT; ++e) {
+      double l = log(dprod[e]);
+      dprod[e] = 1.0;
+#pragma unroll
+      for (int off = 16; off > 0; off >>= 1) l += __shfl_xor_sync(0xffffffffu, l, off);
+      if (lane == 0) s_sums[(warp + LK_NWARPS * e) * 2 + 1] += l;
+    }
+  };
 
   // issue the global->shared copies of one chunk: factor rows (first two), pixel scalars, M tile
   auto prefetch = [&](int chunk) {
     const int p = chunk * LK_KC + lane;
     if (p < n) {
 #pragma unroll
-      for (int e = 0; e < 8; ++e) {
-        const int s = warp + 8 * e;
+      for (int e = 0; e < LK_EPT; ++e) {
+        const int s = warp + LK_NWARPS * e;
         if (tile_s0 + s < sp.num_samples) {
           cp_async8(my_stg + e * LK_THREADS, sp.base0 + (size_t)s_rows[s] * sp.ld + p);
           if (num_rows > 1)
-            cp_async8(my_stg + (8 + e) * LK_THREADS, sp.cache + (size_t)s_rows[LK_TS + s] * sp.ld + p);
+            cp_async8(my_stg + (LK_EPT + e) * LK_THREADS, sp.cache + (size_t)s_rows[LK_TS + s] * sp.ld + p);
         }
       }
-      cp_async8(my_stg + 16 * LK_THREADS, sp.y + p);
-      cp_async8(my_stg + 17 * LK_THREADS, sp.mu + p);
-      cp_async8(my_stg + 18 * LK_THREADS, sp.omega2 + p);
-      cp_async8(my_stg + 19 * LK_THREADS, sp.v + p);
+      cp_async8(my_stg + (2 * LK_EPT + 0) * LK_THREADS, sp.y + p);
+      cp_async8(my_stg + (2 * LK_EPT + 1) * LK_THREADS, sp.mu + p);
+      cp_async8(my_stg + (2 * LK_EPT + 2) * LK_THREADS, sp.omega2 + p);
+      cp_async8(my_stg + (2 * LK_EPT + 3) * LK_THREADS, sp.v + p);
     }
     // M tile: 640 doubles = 320 x 16 B, zero-filled beyond pixel n
     double* Mt = s_mr + (chunk % 3) * (LK_KC * LK_MSTRIDE);
@@ -207,17 +223,17 @@ sample_likelihood_kernel(const LikelihoodSpectrum* __restrict__ specs) {
     const bool pv = p < n;
     double yp = 0, mup = 0, omp = 0, vp = 1;
     if (pv) {
-      yp = my_stg[16 * LK_THREADS]; mup = my_stg[17 * LK_THREADS];
-      omp = my_stg[18 * LK_THREADS]; vp = my_stg[19 * LK_THREADS];
+      yp = my_stg[(2 * LK_EPT + 0) * LK_THREADS]; mup = my_stg[(2 * LK_EPT + 1) * LK_THREADS];
+      omp = my_stg[(2 * LK_EPT + 2) * LK_THREADS]; vp = my_stg[(2 * LK_EPT + 3) * LK_THREADS];
     }
 #pragma unroll
-    for (int e = 0; e < 8; ++e) {
-      const int s = warp + 8 * e;
+    for (int e = 0; e < LK_EPT; ++e) {
+      const int s = warp + LK_NWARPS * e;
       double w = 0.0, g = 0.0;
       if (pv && tile_s0 + s < sp.num_samples) {
         // absorption = product of the factors' profiles, left to right (dla_gp.py:370-386)
         double a = my_stg[e * LK_THREADS];
-        if (num_rows > 1) a = a * my_stg[(8 + e) * LK_THREADS];
+        if (num_rows > 1) a = a * my_stg[(LK_EPT + e) * LK_THREADS];
         for (int r = 2; r < num_rows; ++r) a = a * sp.cache[(size_t)s_rows[r * LK_TS + s] * sp.ld + p];
         if (sp.prod_out) sp.prod_out[(size_t)(tile_s0 + s) * sp.ld + p] = a;
         const double a2 = a * a;
@@ -232,42 +248,51 @@ sample_likelihood_kernel(const LikelihoodSpectrum* __restrict__ specs) {
       Ws[s * LK_WSTRIDE + lane] = w;
       Gs[s * LK_WSTRIDE + lane] = g;
     }
-    // fold the running product of d into the log-determinant every 8 chunks (range safety)
-    if ((chunk & 7) == 7) {
-#pragma unroll
-      for (int e = 0; e < 8; ++e) { ld_acc[e] += log(dprod[e]); dprod[e] = 1.0; }
-    }
+    if ((chunk & 7) == 7) fold_logdet();  // keeps the product of d within range
   };
 
-  auto consume = [&](int chunk, int buf) {
+  // NPAIR Gram blocks followed by NPROJ projection blocks, both compile-time: the three warp
+  // classes (0..5: 4+0, 6: 3+1, 7: 0+2) get separate loop bodies - a predicated-off DMMA still
+  // costs its tensor-pipe slot.
+  auto consume_kind = [&](int chunk, int buf, auto npair_c, auto nproj_c) {
+    constexpr int NPAIR = decltype(npair_c)::value;
+    constexpr int NPROJ = decltype(nproj_c)::value;
     const double* Ws = s_wg + buf * (2 * LK_TS * LK_WSTRIDE);
     const double* Gs = Ws + LK_TS * LK_WSTRIDE;
     const double* Ms = s_mr + (chunk % 3) * (LK_KC * LK_MSTRIDE);
-    const int arow = (mhalf * 32 + grp) * LK_WSTRIDE + tig;
+    const int arow = grp * LK_WSTRIDE + tig;
 #pragma unroll
     for (int kb = 0; kb < LK_KC / 4; ++kb) {
-      double aw[4], ag[4];
-#pragma unroll
-      for (int m = 0; m < 4; ++m) aw[m] = Ws[arow + m * 8 * LK_WSTRIDE + kb * 4];
-      if (quarter == 3) {
-#pragma unroll
-        for (int m = 0; m < 4; ++m) ag[m] = Gs[arow + m * 8 * LK_WSTRIDE + kb * 4];
-      }
       const double* mrow = Ms + (kb * 4 + tig) * LK_MSTRIDE;
+      if (NPAIR > 0) {
+        double aw[LK_MB];
 #pragma unroll
-      for (int nb = 0; nb < 8; ++nb) {
-        if (quarter == 3 && nb >= 6) continue;  // only 30 column blocks exist
-        if (quarter == 3 && nb >= 3) {
-          const double b = mrow[col_j[nb]];
+        for (int m = 0; m < LK_MB; ++m) aw[m] = Ws[arow + m * 8 * LK_WSTRIDE + kb * 4];
 #pragma unroll
-          for (int m = 0; m < 4; ++m) dmma884(acc[m][nb][0], acc[m][nb][1], ag[m], b);
-        } else {
+        for (int nb = 0; nb < NPAIR; ++nb) {
           const double b = mrow[col_i[nb]] * mrow[col_j[nb]];
 #pragma unroll
-          for (int m = 0; m < 4; ++m) dmma884(acc[m][nb][0], acc[m][nb][1], aw[m], b);
+          for (int m = 0; m < LK_MB; ++m) dmma884(acc[m][nb][0], acc[m][nb][1], aw[m], b);
+        }
+      }
+      if (NPROJ > 0) {
+        double ag[LK_MB];
+#pragma unroll
+        for (int m = 0; m < LK_MB; ++m) ag[m] = Gs[arow + m * 8 * LK_WSTRIDE + kb * 4];
+#pragma unroll
+        for (int nb = NPAIR; nb < NPAIR + NPROJ; ++nb) {
+          const double b = mrow[col_j[nb]];
+#pragma unroll
+          for (int m = 0; m < LK_MB; ++m) dmma884(acc[m][nb][0], acc[m][nb][1], ag[m], b);
         }
       }
     }
+  };
+  auto consume = [&](int chunk, int buf) {
+    using std::integral_constant;
+    if (warp < 6) consume_kind(chunk, buf, integral_constant<int, 4>(), integral_constant<int, 0>());
+    else if (warp == 6) consume_kind(chunk, buf, integral_constant<int, 3>(), integral_constant<int, 1>());
+    else consume_kind(chunk, buf, integral_constant<int, 0>(), integral_constant<int, 2>());
   };
 
   // ---- main loop: chunk c+2 in flight (cp.async), chunk c+1 being produced, chunk c in the MMAs ----
@@ -286,27 +311,25 @@ sample_likelihood_kernel(const LikelihoodSpectrum* __restrict__ specs) {
     consume(chunk, buf);
     __syncthreads();
   }
+
   // ---- per-sample scalar sums: reduce over the 32 pixel lanes -----------------------------
+  fold_logdet();
 #pragma unroll
-  for (int e = 0; e < 8; ++e) {
+  for (int e = 0; e < LK_EPT; ++e) {
     double q = q_acc[e];
-    double l = ld_acc[e] + log(dprod[e]);
 #pragma unroll
-    for (int off = 16; off > 0; off >>= 1) {
-      q += __shfl_xor_sync(0xffffffffu, q, off);
-      l += __shfl_xor_sync(0xffffffffu, l, off);
-    }
-    if (lane == 0) { s_sums[(warp + 8 * e) * 2] = q; s_sums[(warp + 8 * e) * 2 + 1] = l; }
+    for (int off = 16; off > 0; off >>= 1) q += __shfl_xor_sync(0xffffffffu, q, off);
+    if (lane == 0) s_sums[(warp + LK_NWARPS * e) * 2] = q;
   }
 
   // ---- accumulators -> E[col][sample] (overlays the stage buffers; all reads finished) -----
   double* E = s_main;
 #pragma unroll
-  for (int m = 0; m < 4; ++m) {
-    const int s = mhalf * 32 + m * 8 + grp;
+  for (int m = 0; m < LK_MB; ++m) {
+    const int s = m * 8 + grp;
 #pragma unroll
-    for (int nb = 0; nb < 8; ++nb) {
-      const int blk = quarter * 8 + nb;
+    for (int nb = 0; nb < LK_NB; ++nb) {
+      const int blk = warp * LK_NB + nb;
       if (blk < LK_NBLK) {
         const int col = blk * 8 + tig * 2;
         E[col * LK_EP_STRIDE + s] = acc[m][nb][0];
@@ -319,7 +342,7 @@ sample_likelihood_kernel(const LikelihoodSpectrum* __restrict__ specs) {
   // ---- Cholesky of the bordered matrix [[B, c], [c', q]] : 4 threads per sample ------------
   // E col layout: pair (i,j) at i(i+1)/2 + j ; projection c_j at 216 + j.
   // Row 20 of the bordered factor is z = L^-1 c, so quad = q - z'z (null_gp.py:345-358).
-  {
+  if (tid < LK_TS * 4) {
     const int s = tid >> 2;       // sample of this thread quad
     const int t = tid & 3;
     double* Es = E + s;
@@ -334,9 +357,7 @@ sample_likelihood_kernel(const LikelihoodSpectrum* __restrict__ specs) {
       for (int k = 0; k < j; ++k) { const double l = at(j, k); piv = fma(-l, l, piv); }
       logdet_prod *= piv;
       if ((j % 5) == 4) { logdet += log(logdet_prod); logdet_prod = 1.0; }
-      const double ljj = sqrt(piv);
-      const double inv = 1.0 / ljj;
-      __syncwarp();  // everyone has read row j before the diagonal is overwritten
+      const double inv = 1.0 / sqrt(piv);
       // rows j+1 .. 20 of column j, interleaved over the quad
       for (int i = j + 1 + t; i <= LK_K; i += 4) {
         double x = at(i, j);
@@ -347,7 +368,7 @@ sample_likelihood_kernel(const LikelihoodSpectrum* __restrict__ specs) {
       }
       __syncwarp();
     }
-    // the thread that owned row 20 in column j is t == (20 - j - 1) & 3; sum the partial z'z
+    // row 20 moved round the quad from column to column; sum the partial z'z
     zz += __shfl_xor_sync(0xffffffffu, zz, 1);
     zz += __shfl_xor_sync(0xffffffffu, zz, 2);
     if (t == 0 && tile_s0 + s < sp.num_samples) {
