@@ -192,7 +192,10 @@ def make_spectrum(
     cont = np.ones(num_pixels)
     cont[inside] = np.interp(rest[inside], rw, model["mu"])
     cont[rest < rw[0]] = 0.3
-    cont[rest > rw[-1]] = np.interp(rw[-1], rw, model["mu"]) * np.exp(-(rest[rest > rw[-1]] - rw[-1]) / 40.0) + 1.0
+    # red side: the Ly-alpha emission wing decays to a unit continuum, so the 1310-1325 A
+    # normalisation window sits at 1 like the (normalised) training spectra of the learned model
+    mu_end = np.interp(rw[-1], rw, model["mu"])
+    cont[rest > rw[-1]] = 1.0 + (mu_end - 1.0) * np.exp(-(rest[rest > rw[-1]] - rw[-1]) / 15.0)
 
     # GP draw on the modelled range
     xi = rng.standard_normal(model["M"].shape[1])
@@ -200,11 +203,16 @@ def make_spectrum(
     for j in range(model["M"].shape[1]):
         gp_draw[inside] += np.interp(rest[inside], rw, model["M"][:, j]) * xi[j]
 
-    # mean-flux suppression bluewards of Lya (Kim et al. parameters)
+    # mean-flux suppression by the Lyman-series forest (Kim et al. parameters), the same functional
+    # form the null model applies to its mean (effective_optical_depth.py:51-78)
     lya = params.lya_wavelength
-    z_abs = wavelengths / lya - 1
-    tau_eff = 0.0023 * (1 + z_abs) ** 3.65
-    suppress = np.where(rest < lya, np.exp(-tau_eff), 1.0)
+    tw = tables.TRANSITION_WAVELENGTHS * 1e8
+    tau_eff = np.zeros(num_pixels)
+    for i in range(params.num_forest_lines):
+        z_i = (wavelengths - tw[i]) / tw[i]
+        tau_i = 0.0023 * tables.OSCILLATOR_STRENGTHS[i] / tables.OSCILLATOR_STRENGTHS[0] * tw[i] / tw[0]
+        tau_eff += np.where(z_i <= z_qso, tau_i * np.maximum(1 + z_i, 0.0) ** 3.65, 0.0)
+    suppress = np.exp(-tau_eff)
 
     # injected DLAs
     absorption = np.ones(num_pixels)

@@ -1,0 +1,154 @@
+#!/usr/bin/env python
+"""
+make_golden.py : generate tests/golden/*.npz by running the LIVE, UNMODIFIED reference
+(/root/reference, imported with h5py/emcee stubbed - oracle/ref_loader.py) on seeded synthetic
+inputs.  Run in the build container only (the GPU box has no /root/reference); the vectors
+it writes are committed and are what pins the oracle and the CUDA path to the reference.
+
+    python tests/golden/make_golden.py            # all fixtures (about 2 minutes)
+"""
+import os
+import sys
+import time
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, ROOT)
+
+from oracle import ref_loader  # noqa: E402
+
+ref_loader.load_reference()
+from gpy_dla_detection import voigt as rvoigt  # noqa: E402
+from gpy_dla_detection.effective_optical_depth import effective_optical_depth as r_eod  # noqa: E402
+from gpy_dla_detection.set_parameters import Parameters as RParameters  # noqa: E402
+from gpy_dla_detection.null_gp import NullGP as RNullGP  # noqa: E402
+from gpy_dla_detection.dla_gp import DLAGP as RDLAGP  # noqa: E402
+from gpy_dla_detection.subdla_gp import SubDLAGP as RSubDLAGP  # noqa: E402
+from gpy_dla_detection.bayesian_model_selection import BayesModelSelect as RBayes  # noqa: E402
+
+from gpy_dla_detection_b200 import synthetic  # noqa: E402
+from gpy_dla_detection_b200.set_parameters import Parameters  # noqa: E402
+
+
+def golden_voigt():
+    """voigt.voigt_absorption on a BOSS-like padded grid (a1) + effective optical depth (a2)."""
+    loglam = 3.5523 + 1e-4 * np.arange(4650)
+    wl = 10.0**loglam
+    z_qso = 3.2
+    sel = (wl / (1 + z_qso) >= 911.75) & (wl / (1 + z_qso) <= 1215.75)
+    grid = wl[sel]
+    cases = [(2.6, 20.3, 3, True), (3.05, 21.7, 3, True), (2.2, 19.6, 3, False), (2.9, 20.9, 5, True),
+             (2.45, 22.4, 31, True), (3.1, 19.9, 31, False), (2.0, 20.0, 1, True)]
+    out = {"wavelengths": grid, "cases": np.array(cases, dtype=np.float64)}
+    for i, (zd, ln, nl, br) in enumerate(cases):
+        out["profile_%d" % i] = rvoigt.voigt_absorption(grid, 10.0**ln, zd, num_lines=int(nl), broadening=bool(br))
+    out["eod_kim"] = r_eod(grid, 3.65, 0.0023, z_qso, 31)
+    out["eod_learned"] = r_eod(grid, 3.1, 0.0019, 2.9, 5)
+    # Faddeeva real part at the arguments the profile visits (scipy wofz, the reference's own call)
+    from scipy.special import wofz
+    x = np.concatenate([np.linspace(0, 70, 1401), np.geomspace(70, 2.5e4, 400)])
+    ys = rvoigt.gammas[[0, 1, 2, 4, 9, 30]] / (np.sqrt(2) * rvoigt.sigma)
+    out["fadd_x"] = x
+    out["fadd_y"] = ys
+    out["fadd_re"] = np.stack([np.real(wofz(x + 1j * y)) for y in ys])
+    # the reference's Lyman-series literals themselves (voigt.py:18-224)
+    out["tables"] = np.stack([rvoigt.transition_wavelengths, rvoigt.oscillator_strengths, rvoigt.Gammas,
+                              rvoigt.leading_constants, rvoigt.gammas])
+    out["instrument_profile"] = rvoigt.instrument_profile
+    out["sigma"] = rvoigt.sigma
+    out["c"] = rvoigt.c
+    np.savez_compressed(os.path.join(HERE, "voigt_golden.npz"), **out)
+    print("voigt_golden.npz written")
+
+
+def run_reference(S, z_qso, seed, max_dlas=4, num_lines=3, broadening=True):
+    rp = RParameters(num_dla_samples=S, num_lines=num_lines)
+    p = Parameters(num_dla_samples=S, num_lines=num_lines)
+    model = synthetic.make_learned_model(0)
+    prior = synthetic.SyntheticPrior(p)
+    dla = synthetic.make_dla_sample_arrays(p)
+    sub = synthetic.make_subdla_sample_arrays(p)
+    wl, fl, nv, pm = synthetic.make_spectrum(model, z_qso, seed=seed)
+    rest = rp.emitted_wavelengths(wl, z_qso)
+    margs = (model["rest_wavelengths"], model["mu"], model["M"], model["log_omega"], model["log_c_0"],
+             model["log_tau_0"], model["log_beta"])
+    gp = RNullGP(rp, prior, *margs)
+    dgp = RDLAGP(rp, prior, ref_loader.RefDLASamples(rp, dla), *margs, broadening=broadening)
+    sgp = RSubDLAGP(rp, prior, ref_loader.RefDLASamples(rp, sub, True), *margs, broadening=broadening)
+    for m in (gp, dgp, sgp):
+        m.set_data(rest, fl, nv, pm, z_qso, build_model=True)
+    np.random.seed(0)  # run_bayes_select.py:144
+    bayes = RBayes([0, 1, max_dlas], 2)
+    t0 = time.time()
+    log_post = bayes.model_selection([gp, sgp, dgp], z_qso)
+    dt = time.time() - t0
+    try:
+        map_z, map_n = dgp.maximum_a_posteriori()
+    except ValueError:
+        map_z = map_n = np.full((max_dlas, max_dlas), np.nan)
+    # a few single-sample likelihoods and one this_dla_gp through the reference's own entry points
+    zs = dgp.dla_samples.sample_z_dlas(dgp.this_wavelengths, z_qso)
+    pick = np.array([0, 1, S // 3, S // 2, S - 1])
+    single = np.array([dgp.sample_log_likelihood_k_dlas(np.array([zs[i]]), np.array([dla["nhi_samples"][i]])) for i in pick])
+    pair = np.array([dgp.sample_log_likelihood_k_dlas(np.array([zs[i], zs[(i * 7 + 3) % S]]),
+                                                      np.array([dla["nhi_samples"][i], dla["nhi_samples"][(i * 7 + 3) % S]]))
+                     for i in pick])
+    dmu, dM, dom = dgp.this_dla_gp(np.array([zs[pick[2]], zs[pick[3]]]),
+                                   np.array([dla["nhi_samples"][pick[2]], dla["nhi_samples"][pick[3]]]))
+    out = dict(
+        S=S, z_qso=z_qso, seed=seed, max_dlas=max_dlas, num_lines=num_lines, broadening=broadening,
+        wavelengths=wl, flux=fl, noise_variance=nv, pixel_mask=pm,
+        x=gp.x, y=gp.y, v=gp.v, ind=gp.ind, ind_unmasked=gp.ind_unmasked,
+        this_wavelengths=gp.this_wavelengths, unmasked_wavelengths=gp.unmasked_wavelengths,
+        padded_wavelengths=gp.padded_wavelengths, this_mu=gp.this_mu, this_M=gp.this_M, this_omega2=gp.this_omega2,
+        normalization_median=gp.normalization_median,
+        log_priors=bayes.log_priors, log_likelihoods=bayes.log_likelihoods, log_posteriors=log_post,
+        model_posteriors=bayes.model_posteriors, p_dla=bayes.p_dla, p_no_dla=bayes.p_no_dla,
+        sample_log_likelihoods_dla=dgp.sample_log_likelihoods, base_sample_inds=dgp.base_sample_inds,
+        sample_log_likelihoods_lls=sgp.sample_log_likelihoods[:, 0],
+        MAP_z_dlas=map_z, MAP_log_nhis=map_n,
+        min_z_dla=rp.min_z_dla(wl, z_qso), max_z_dla=rp.max_z_dla(wl, z_qso),
+        sample_z_dlas=zs, pick=pick, single_ll=single, pair_ll=pair, this_dla_mu=dmu, this_dla_M=dM,
+        this_dla_omega2=dom, prior_counts=np.array(prior.less_ind(z_qso), dtype=np.float64),
+        reference_seconds=dt,
+    )
+    return out
+
+
+def golden_spectra():
+    cases = [
+        ("spec_S256_z2p3", dict(S=256, z_qso=2.3, seed=11)),
+        ("spec_S300_z3p0", dict(S=300, z_qso=3.0, seed=7)),
+        ("spec_S256_z4p4", dict(S=256, z_qso=4.4, seed=23)),
+        ("spec_S200_z2p8_lines5_nobroad", dict(S=200, z_qso=2.8, seed=5, num_lines=5, broadening=False)),
+        ("spec_S200_z3p4_max2", dict(S=200, z_qso=3.4, seed=31, max_dlas=2)),
+    ]
+    for name, kw in cases:
+        out = run_reference(**kw)
+        np.savez_compressed(os.path.join(HERE, name + ".npz"), **out)
+        print(name, "reference time %.1f s" % out["reference_seconds"], "p_dla", out["p_dla"])
+
+
+def golden_full():
+    """One spectrum at the full published size: S = 10 000, max_dlas = 4 (config 1 of BASELINE.json)."""
+    out = run_reference(S=10000, z_qso=2.9, seed=3)
+    # inputs are regenerated from the seeds by the tests; keep outputs only (float32 would lose parity)
+    keep = ("S", "z_qso", "seed", "max_dlas", "num_lines", "broadening", "log_priors", "log_likelihoods",
+            "log_posteriors", "model_posteriors", "p_dla", "sample_log_likelihoods_dla", "base_sample_inds",
+            "sample_log_likelihoods_lls", "MAP_z_dlas", "MAP_log_nhis", "min_z_dla", "max_z_dla", "ind",
+            "ind_unmasked", "this_mu", "this_omega2", "normalization_median", "prior_counts", "reference_seconds",
+            "wavelengths", "flux", "noise_variance", "pixel_mask")
+    np.savez_compressed(os.path.join(HERE, "spec_S10000_z2p9_full.npz"), **{k: out[k] for k in keep})
+    print("full: reference time %.1f s" % out["reference_seconds"], "p_dla", out["p_dla"])
+
+
+if __name__ == "__main__":
+    if "--only-voigt" in sys.argv:
+        golden_voigt()
+        sys.exit(0)
+    golden_voigt()
+    golden_spectra()
+    if "--no-full" not in sys.argv:
+        golden_full()
