@@ -258,3 +258,79 @@ def process_qso(
     out = proc.process(offsets, wl, fl, nv, pm, np.asarray(z_qso_list, dtype=np.float64), keep_samples=keep_samples)
     out["z_qsos"] = np.asarray(z_qso_list, dtype=np.float64)
     return out
+
+
+# ---------------------------------------------------------------------------------------------------
+# multi-GPU: spectra are independent, so a catalogue is block-partitioned over the ranks
+# (one process per GPU); there is no collective on the data path, only a final gather of the
+# (num_quasars, ...) result arrays on rank 0 - the in-box replacement of the reference's SLURM
+# job array + sbatch_reunion merge (slurm/submit_gp_find_lls.sh, CDDF_analysis/sbatch_reunion.py:13-63).
+# ---------------------------------------------------------------------------------------------------
+def gather_results(local: Dict[str, np.ndarray], num_items: int, rank: int, world_size: int,
+                   group=None) -> Optional[Dict[str, np.ndarray]]:
+    """
+    Concatenate the per-rank result dictionaries in spectrum order on rank 0 (None elsewhere).
+    Every array whose leading dimension is the rank's shard length is gathered; the shards
+    must follow `shard_range`.  A rank with an empty shard passes an empty dictionary.
+    """
+    if world_size == 1:
+        return local
+    import torch.distributed as dist
+
+    start, stop = shard_range(num_items, rank, world_size)
+    mine = {k: v for k, v in local.items()
+            if stop > start and isinstance(v, np.ndarray) and v.ndim >= 1 and v.shape[0] == stop - start}
+    parts = [None] * world_size if rank == 0 else None
+    dist.gather_object(mine, parts, dst=0, group=group)
+    if rank != 0:
+        return None
+    keys = None
+    for r, part in enumerate(parts):
+        a, b = shard_range(num_items, r, world_size)
+        if b == a:
+            continue
+        if keys is None:
+            keys = sorted(part.keys())
+        if sorted(part.keys()) != keys:
+            raise RuntimeError("rank %d returned a different set of result arrays" % r)
+        for k in keys:
+            if part[k].shape[0] != b - a:
+                raise RuntimeError("rank %d: array %s has %d rows for a shard of %d" % (r, k, part[k].shape[0], b - a))
+    if keys is None:
+        return {}
+    return {k: np.concatenate([part[k] for part in parts if part], axis=0) for k in keys}
+
+
+def process_qso_sharded(
+    qso_list: List,
+    z_qso_list: List,
+    read_spec: Callable,
+    max_dlas: int = 4,
+    broadening: bool = True,
+    *,
+    rank: Optional[int] = None,
+    world_size: Optional[int] = None,
+    group=None,
+    process_fn: Optional[Callable] = None,
+    **kwargs,
+) -> Optional[Dict[str, np.ndarray]]:
+    """
+    `process_qso` over the ranks of an initialised torch.distributed job (one rank per GPU):
+    rank r reads and processes the spectra of shard_range(Q, r, world_size) on its own device
+    and rank 0 returns the whole catalogue (None on the other ranks).  `process_fn` defaults
+    to `process_qso`.
+    """
+    import os
+
+    if rank is None:
+        rank = int(os.environ.get("RANK", "0"))
+    if world_size is None:
+        world_size = int(os.environ.get("WORLD_SIZE", "1"))
+    Q = len(qso_list)
+    assert len(z_qso_list) == Q
+    start, stop = shard_range(Q, rank, world_size)
+    fn = process_fn or process_qso
+    local = {}
+    if stop > start:
+        local = fn(qso_list[start:stop], z_qso_list[start:stop], read_spec, max_dlas, broadening, **kwargs)
+    return gather_results(local, Q, rank, world_size, group)
