@@ -121,6 +121,27 @@ def test_spectrum_golden(path):
         assert abs(got - ref) < 1e-9 * abs(ref)
 
 
+def test_full_size_spectrum_golden_oracle():
+    """S = 10 000, max_dlas = 4 (config 1/2 size): the restatement against the live reference's output (~30 s)"""
+    from tests import helpers as H
+
+    g = load("spec_S10000_z2p9_full.npz")
+    st = H.Setup(10000, 3)
+    out = O.process_spectrum(st.model, st.dla, st.sub, tuple(g["prior_counts"]), g["wavelengths"], g["flux"],
+                             g["noise_variance"], g["pixel_mask"], float(g["z_qso"]), 4, 3, True)
+    ref_ll = g["sample_log_likelihoods_dla"]
+    assert np.array_equal(out["prep"]["ind"], g["ind"]) and np.array_equal(out["prep"]["ind_unmasked"], g["ind_unmasked"])
+    assert np.array_equal(np.isnan(out["sample_log_likelihoods_dla"]), np.isnan(ref_ll))
+    assert H.ll_err(out["sample_log_likelihoods_dla"], ref_ll) < 1e-9
+    assert H.ll_err(out["sample_log_likelihoods_lls"], g["sample_log_likelihoods_lls"]) < 1e-9
+    assert np.array_equal(out["base_sample_inds"], g["base_sample_inds"])  # 30 000 resampled indices, bit-exact
+    for k in ("log_priors", "log_likelihoods", "log_posteriors", "model_posteriors"):
+        assert np.max(np.abs(out[k] - g[k])) < 1e-6, k
+    assert abs(out["p_dla"] - float(g["p_dla"])) < 1e-6
+    assert np.array_equal(out["MAP_z_dlas"], g["MAP_z_dlas"], equal_nan=True)
+    assert np.array_equal(out["MAP_log_nhis"], g["MAP_log_nhis"], equal_nan=True)
+
+
 def test_batch_likelihood_matches_literal_form():
     """the BLAS-friendly batch used by the oracle == the literal restatement of null_gp.py:307-360"""
     g = np.load(spectrum_fixtures()[0])
