@@ -162,32 +162,6 @@ int main(int argc, char** argv) {
   double tf_mma_lo = (double)sms * 4 * iters * 16 * 512.0 / (ms_mma_lo * 1e-3) / 1e12;
   double ms_mma_md = time_ms([&] { k_dmma884<16><<<sms, 256>>>(out, 1.0000001, 1e-9, iters); }, 10);
   double tf_mma_md = (double)sms * 8 * iters * 16 * 512.0 / (ms_mma_md * 1e-3) / 1e12;
-// ---- mixed: are the DFMA pipe and the DMMA tensor sub-pipe independent units? ------------------
-template <int NMMA, int NFMA>
-__global__ void __launch_bounds__(256) k_mixed(double* out, double a, double b, int iters) {
-  double c0[NMMA], c1[NMMA], acc[NFMA];
-#pragma unroll
-  for (int i = 0; i < NMMA; ++i) { c0[i] = i; c1[i] = -i; }
-#pragma unroll
-  for (int i = 0; i < NFMA; ++i) acc[i] = threadIdx.x * 1e-3 + i;
-  double fa = a + threadIdx.x * 1e-9, fb = b;
-  for (int it = 0; it < iters; ++it) {
-#pragma unroll
-    for (int i = 0; i < NMMA; ++i) {
-      asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
-                   : "+d"(c0[i]), "+d"(c1[i]) : "d"(fa), "d"(fb));
-#pragma unroll
-      for (int j = 0; j < NFMA / NMMA; ++j) acc[i * (NFMA / NMMA) + j] = fma(acc[i * (NFMA / NMMA) + j], a, b);
-    }
-  }
-  double s = 0;
-#pragma unroll
-  for (int i = 0; i < NMMA; ++i) s += c0[i] + c1[i];
-#pragma unroll
-  for (int i = 0; i < NFMA; ++i) s += acc[i];
-  if (s == 123.456) out[0] = s;
-}
-
 #ifdef TRY_M16
   double ms_m16 = time_ms([&] { k_dmma1688<8><<<blocks, threads>>>(out, 1.0000001, 1e-9, iters); }, 10);
   double tf_m16 = nwarps * iters * 8 * (16.0 * 8 * 8 * 2) / (ms_m16 * 1e-3) / 1e12;

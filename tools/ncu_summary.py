@@ -1,11 +1,12 @@
 #!/usr/bin/env python
-"""Summarise an .ncu-rep (first captured launch): headline metrics, stall reasons, hottest SASS lines."""
+"""Summarise one launch of an .ncu-rep (usage: ncu_summary.py REP [TOP_N] [LAUNCH_INDEX]): headline metrics, stall reasons, hottest SASS lines."""
 import csv, collections, subprocess, sys, io
 rep = sys.argv[1]
 top_n = int(sys.argv[2]) if len(sys.argv) > 2 else 16
+launch = int(sys.argv[3]) if len(sys.argv) > 3 else 0   # which captured launch (0-based)
 raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
 rows = list(csv.reader(io.StringIO(raw)))
-hdr, units, vals = rows[0], rows[1], rows[2]
+hdr, units, vals = rows[0], rows[1], rows[2 + launch]
 def g(name):
     for i, k in enumerate(hdr):
         if k == name: return vals[i] + " " + units[i]
@@ -25,7 +26,8 @@ for i, k in enumerate(hdr):
         except ValueError: pass
 tot = sum(st.values()) or 1
 print("stall reasons (pc samples): " + ", ".join("%s %.1f%%" % (k, 100.0 * v / tot) for k, v in sorted(st.items(), key=lambda t: -t[1])[:8]))
-src = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"], capture_output=True, text=True).stdout
+src = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--launch-skip", str(launch), "--launch-count", "1"],
+                     capture_output=True, text=True).stdout
 rows = list(csv.reader(io.StringIO(src)))
 hdr = rows[1]
 isrc, isamp, iexe = hdr.index("Source"), hdr.index("# Samples"), hdr.index("Instructions Executed")
