@@ -80,6 +80,8 @@ struct dla_catalogue {
   DevBuf<int32_t> uidx;
   DevBuf<double> z_samples, cache, prod, raw_ll0, raw_ll, sample_ll_dla, sample_ll_sub, log_ev_dla, log_ev_sub, cdf;
   DevBuf<double> log_lik, log_priors, log_post, model_post, p_dla, p_no_dla, map_z, map_lognhi;
+  DevBuf<double> basis;  // Gram basis panels of the batch's spectra
+  DevBuf<GramBasisTask> basis_desc;
   DevBuf<int32_t> rows, inds_t, map_ind;
   DevBuf<int> alive;  // [B][4] : DLA level-loop alive flag, status, usable (constant), pad
   DevBuf<PrepTask> prep_desc;
@@ -302,9 +304,9 @@ extern "C" int dla_catalogue_run_staged(dla_catalogue* cat, dla_catalogue_output
 
     // ---- 2. sizes, cache layout, descriptors ---------------------------------------------------
     std::vector<int> n_b(nb), nu_b(nb), ld_b(nb);
-    std::vector<size_t> cache_off(nb), prod_off(nb);
-    size_t cache_total = 0, prod_total = 0;
-    int max_n_abs = 1;
+    std::vector<size_t> cache_off(nb), prod_off(nb), basis_off(nb);
+    size_t cache_total = 0, prod_total = 0, basis_total = 0;
+    int max_n_abs = 1, max_basis_rows = LK_KC;
     for (int b = 0; b < nb; ++b) {
       nu_b[b] = (int)h_scalars[(size_t)b * 8 + 0];
       n_b[b] = (int)h_scalars[(size_t)b * 8 + 1];
@@ -314,9 +316,22 @@ extern "C" int dla_catalogue_run_staged(dla_catalogue* cat, dla_catalogue_output
       prod_off[b] = prod_total;
       if (md >= 3) prod_total += (size_t)S * ld_b[b];
       max_n_abs = std::max(max_n_abs, cat->params.broadening ? nu_b[b] + 2 * w : nu_b[b]);
+      const size_t brows = round_up((size_t)std::max(n_b[b], 1), LK_KC);
+      basis_off[b] = basis_total;
+      basis_total += brows * LK_PSTRIDE;
+      max_basis_rows = std::max(max_basis_rows, (int)brows);
     }
     DLA_CUDA(cat->cache.ensure(cache_total));
     DLA_CUDA(cat->prod.ensure(prod_total));
+    DLA_CUDA(cat->basis.ensure(basis_total));
+    DLA_CUDA(cat->basis_desc.ensure(nb));
+    std::vector<GramBasisTask> h_basis(nb);
+    for (int b = 0; b < nb; ++b) {
+      h_basis[b].M = h_prep[b].M;
+      h_basis[b].P = cat->basis.p + basis_off[b];
+      h_basis[b].n = n_b[b];
+    }
+    DLA_CUDA(cudaMemcpyAsync(cat->basis_desc.p, h_basis.data(), sizeof(GramBasisTask) * nb, cudaMemcpyHostToDevice, rt.stream));
 
     h_grid.resize(nb);
     h_lk.assign((size_t)nb * md, LikelihoodSpectrum());
@@ -348,6 +363,7 @@ extern "C" int dla_catalogue_run_staged(dla_catalogue* cat, dla_catalogue_output
         d.mu = h_prep[b].mu;
         d.omega2 = h_prep[b].omega2;
         d.M = h_prep[b].M;
+        d.P = cat->basis.p + basis_off[b];
         d.cache = cache_b;
         d.rows0 = nullptr;
         d.alive = cat->alive.p + (size_t)b * 4;
@@ -457,6 +473,8 @@ extern "C" int dla_catalogue_run_staged(dla_catalogue* cat, dla_catalogue_output
       init_rows_kernel<<<grid, 256, 0, rt.stream>>>(cat->rows.p, S, md, cat->grid_desc.p);
       DLA_LAUNCHED();
     }
+    gram_basis_kernel<<<dim3((unsigned)((max_basis_rows + 7) / 8), nb), 256, 0, rt.stream>>>(cat->basis_desc.p);
+    DLA_LAUNCHED();
     {
       dim3 grid((2 * S + 255) / 256, nb);
       z_samples_kernel<<<grid, 256, 0, rt.stream>>>(cat->scalars.p, 8, cat->dla_offsets.p, cat->sub_offsets.p, S, cat->z_samples.p);

@@ -161,6 +161,10 @@ struct dla_spectrum {
   DevBuf<LikelihoodSpectrum> lk_desc;
   DevBuf<EvidenceLevel> ev_desc;
   DevBuf<AbsorptionGrid> grid_desc;
+  // Gram basis [P | M] of the likelihood kernel (built on first use)
+  DevBuf<double> basis;
+  DevBuf<GramBasisTask> basis_desc;
+  bool basis_ready = false;
 };
 
 // ------------------------------------------------------------------------------------------
@@ -195,6 +199,25 @@ static int launch_voigt(dla_spectrum* sp, const double* d_z, const double* d_nhi
 
 static int ensure_cache(dla_spectrum* sp, size_t rows) {
   DLA_CUDA(sp->cache.ensure(rows * (size_t)sp->ld));
+  return 0;
+}
+
+// Gram basis of the spectrum's interpolated M (pair products + M columns), streamed by the
+// likelihood kernel in 16-pixel panels
+static int ensure_basis(dla_spectrum* sp) {
+  if (sp->basis_ready) return 0;
+  Runtime& rt = runtime();
+  const size_t rows = round_up((size_t)std::max(sp->n, 1), LK_KC);
+  DLA_CUDA(sp->basis.ensure(rows * LK_PSTRIDE));
+  DLA_CUDA(sp->basis_desc.ensure(1));
+  GramBasisTask t;
+  t.M = sp->M.p;
+  t.P = sp->basis.p;
+  t.n = sp->n;
+  DLA_CUDA(cudaMemcpyAsync(sp->basis_desc.p, &t, sizeof(t), cudaMemcpyHostToDevice, rt.stream));
+  gram_basis_kernel<<<dim3((unsigned)((rows + 7) / 8), 1), 256, 0, rt.stream>>>(sp->basis_desc.p);
+  DLA_LAUNCHED();
+  sp->basis_ready = true;
   return 0;
 }
 
@@ -619,6 +642,7 @@ static LikelihoodSpectrum base_desc(dla_spectrum* sp) {
   d.mu = sp->mu.p;
   d.omega2 = sp->omega2.p;
   d.M = sp->M.p;
+  d.P = sp->basis.p;
   d.base0 = sp->cache.p;
   d.cache = sp->cache.p;
   d.rows0 = nullptr;
@@ -649,6 +673,7 @@ extern "C" int dla_null_log_model_evidence(dla_spectrum* sp, double* out) {
   DLA_REQUIRE(sp && out, "null pointer argument");
   DLA_REQUIRE(sp->k == LK_K, "the batched likelihood path is built for k = 20");
   DLA_REQUIRE(sp->n >= 1, "spectrum has no modelled pixels");
+  if (int rcb = ensure_basis(sp)) return rcb;
   DevBuf<double> ones, res;
   DLA_CUDA(ones.alloc(sp->ld));
   DLA_CUDA(res.alloc(1));
@@ -693,6 +718,7 @@ extern "C" int dla_sample_log_likelihoods(dla_spectrum* sp, const double* z_dlas
   DLA_CUDA(sp->nhi_dev.upload(nt.data(), rows, rt.stream));
   int rc = ensure_cache(sp, rows);
   if (rc) return rc;
+  if ((rc = ensure_basis(sp))) return rc;
   DLA_CUDA(sp->raw_ll.ensure(S));
   KernelTimer timer;
   DLA_CUDA(timer.begin());
@@ -761,6 +787,7 @@ extern "C" int dla_log_model_evidences(dla_spectrum* sp, const double* z_samples
   }
   int rc = ensure_cache(sp, S);
   if (rc) return rc;
+  if ((rc = ensure_basis(sp))) return rc;
   if (max_dlas >= 3) DLA_CUDA(sp->prod.ensure((size_t)S * sp->ld));
   DLA_CUDA(sp->raw_ll.ensure(S));
   DLA_CUDA(sp->sample_ll.ensure((size_t)S * max_dlas));

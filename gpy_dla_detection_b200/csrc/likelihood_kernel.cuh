@@ -5,35 +5,57 @@
 // d = omega2 a^2 + v (dla_gp.py:388-394) and calls NullGP.log_mvnpdf_low_rank
 // (null_gp.py:307-360): B = I + M'D^-1 M (dgemm), chol(B), quad and log-det.
 //
-// Here all samples of a tile share the interpolated model, so with
+// Here all samples of a spectrum share the interpolated model, so with
 //     w_sp = a_sp^2 / d_sp ,  g_sp = a_sp r_sp / d_sp ,  r_sp = y_p - mu_p a_sp
-// the per-sample Gram matrices and projections are ONE dense FP64 contraction
+// the per-sample Gram matrices and projections are ONE dense FP64 contraction over pixels
 //     [B_s - I | c_s] = [W | G] x [P | M] ,   P[p,(i,j)] = m_pi m_pj  (i >= j, 210 pairs)
-// over the pixel axis, run on the FP64 tensor path (DMMA m8n8k4; B200 measures 36.9 TFLOP/s,
-// same as the DFMA pipe, at a fraction of the issue slots).  W/G tiles are produced on the
-// fly from the profile cache (product of up to 4 absorber rows, dla_gp.py:370-386), P is
-// formed in registers from the staged M tile, and the k x k Cholesky factor / solve /
-// log-det of every sample of the tile runs in shared memory straight out of the accumulator
-// fragments.  HBM sees only the profile rows (read) and one double per sample (written).
+// on the FP64 tensor path (DMMA m8n8k4; on B200 it shares the 64 FMA lanes/SM/clk of the DFMA
+// pipe - 37 TFLOP/s measured either way - so every scalar FP64 instruction in this kernel is
+// paid for with DMMA slots).  Structure, per CTA of 32 samples x 8 warps (two CTAs per SM):
+//   * the Gram basis [P | M] of the spectrum (n x 240, precomputed once by gram_basis_kernel,
+//     L2-resident) streams through shared memory in 16-pixel panels by TMA bulk copies
+//     (cp.async.bulk + mbarrier complete_tx): no DMUL and no column-index registers in the MMA loop;
+//   * every warp is producer AND consumer (warps that only produce starve behind warps that only
+//     issue DMMAs - measured): it turns its 2 x 16 share of the profile-cache rows (product of up to
+//     8 absorber factors, dla_gp.py:370-386, prefetched one panel ahead in registers) into the W / G
+//     operand tiles of the NEXT panel - MUFU-seeded Newton reciprocal, integer-renormalised running
+//     product for sum log d (one log per lane per tile) - then runs its DMMAs on the current one;
+//   * warp (rh, cq) owns 16 samples x 7 or 8 of the 30 column blocks, sized [8,7,8,7] / [7,8,7,8]
+//     so that the two warps of every SM sub-partition issue 30 DMMAs per 4 pixels: no padding
+//     block, four balanced FP64 pipes;
+//   * hand-over between panels by mbarriers (full: 8 warp arrivals + the TMA byte count; empty:
+//     8 warp arrivals), split-phase, so warps drift by up to a panel instead of meeting at a
+//     CTA-wide barrier;
+//   * the bordered 21 x 21 Cholesky (factor, z = L^-1 c, log-det) of every sample runs in shared
+//     memory straight out of the accumulator fragments while the SM's other CTA keeps the
+//     tensor pipe busy.
+// HBM sees only the profile rows (read) and one double per sample (written).
 #pragma once
 #include <stdint.h>
 #include <type_traits>
 
 namespace dla {
 
-constexpr int LK_K = 20;                        // rank of the learned covariance (Parameters.k)
+constexpr int LK_K = 20;                         // rank of the learned covariance (Parameters.k)
 constexpr int LK_PAIRS = LK_K * (LK_K + 1) / 2;  // 210 lower-triangle pairs
-constexpr int LK_TS = 32;                        // samples per CTA tile (two CTAs share an SM)
-constexpr int LK_KC = 32;                        // pixels per chunk
-constexpr int LK_WSTRIDE = LK_KC + 4;            // padded row stride of the W/G tiles (conflict-free DMMA A loads)
-constexpr int LK_MSTRIDE = LK_K;                 // row stride of the M tile (20 == 4 mod 16: conflict-free B loads)
-constexpr int LK_THREADS = 256;
+constexpr int LK_TS = 32;                        // samples per CTA tile
+constexpr int LK_KC = 16;                        // pixels per panel
+constexpr int LK_WSTRIDE = LK_KC + 4;            // row stride of the W/G tiles (20 == 4 mod 16: conflict-free A loads)
 constexpr int LK_NBLK_PAIR = 27;                 // ceil(210 / 8) column blocks of the Gram part
 constexpr int LK_NBLK = 30;                      // + 3 column blocks (24 >= 20) of the projection part
-constexpr int LK_EP_COLS = 216 + 24;             // columns staged for the epilogue
+constexpr int LK_NCOLS = LK_NBLK * 8;            // 240
+constexpr int LK_PSTRIDE = LK_NCOLS + 4;         // basis row stride (244 == 4 mod 16: conflict-free B loads)
+constexpr int LK_PROJ_COL0 = LK_NBLK_PAIR * 8;   // 216: first projection column
+constexpr int LK_WARPS = 8;
+constexpr int LK_THREADS = LK_WARPS * 32;        // 256
+constexpr int LK_STAGES = 2;
 constexpr int LK_EP_STRIDE = LK_TS + 1;          // epilogue smem: [col][sample], stride 33
 constexpr int LK_MAX_ROWS = 8;                   // max absorbers multiplied per sample (max_dlas <= 8)
+constexpr int LK_MB = 2;                         // DMMA row blocks per warp (16 samples)
+constexpr int LK_NB_MAX = 8;                     // DMMA column blocks per warp (7 or 8)
+constexpr int LK_EPT = LK_TS * LK_KC / LK_THREADS;  // W/G elements per thread per panel (2)
 constexpr double LK_LOG_2PI = 1.83787706640934534;  // null_gp.py:325
+constexpr double LK_LN2 = 0.693147180559945309417232121458;
 
 // pair index c -> (i, j), i >= j, row-major lower triangle; pads map to (0,0)
 __device__ __constant__ uint8_t c_pair_i[LK_NBLK_PAIR * 8];
@@ -54,6 +76,7 @@ struct LikelihoodSpectrum {
   const double* mu;      // n   this_mu  (mean-flux suppressed)
   const double* omega2;  // n   this_omega2
   const double* M;       // n x 20 row-major this_M
+  const double* P;       // Gram basis [ceil(n/16)*16][244]: 210 pair products, pad, 20 columns of M, pad; zero rows >= n
   const double* base0;   // profile rows of factor 0, stride ld
   const double* cache;   // profile rows of factors >= 1, stride ld
   const int32_t* rows0;  // factor-0 row per sample, or nullptr
@@ -69,69 +92,113 @@ struct LikelihoodSpectrum {
   int row0;              // first profile row when the row arrays are null
 };
 
-__device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double b) {
-  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
-               : "+d"(c0), "+d"(c1)
-               : "d"(a), "d"(b));
+// ---- Gram basis of one spectrum: P[p][c] = m_p,i(c) * m_p,j(c), then the columns of M ---------------
+struct GramBasisTask {
+  const double* M;  // n x 20
+  double* P;        // [ceil(n/16)*16][LK_PSTRIDE]
+  int n;
+};
+// grid = (ceil(max_rows / 8), num_spectra), block = 256 (8 pixel rows x 32 lanes)
+__global__ void __launch_bounds__(256) gram_basis_kernel(const GramBasisTask* __restrict__ tasks) {
+  const GramBasisTask t = tasks[blockIdx.y];
+  const int rows = (t.n + LK_KC - 1) / LK_KC * LK_KC;
+  const int p = blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (p >= rows) return;
+  const int lane = threadIdx.x & 31;
+  const double* m = t.M + (size_t)p * LK_K;
+  double* out = t.P + (size_t)p * LK_PSTRIDE;
+  for (int c = lane; c < LK_PSTRIDE; c += 32) {
+    double val = 0.0;
+    if (p < t.n) {
+      if (c < LK_PAIRS) val = __dmul_rn(m[c_pair_i[c]], m[c_pair_j[c]]);
+      else if (c >= LK_PROJ_COL0 && c < LK_PROJ_COL0 + LK_K) val = m[c - LK_PROJ_COL0];
+    }
+    out[c] = val;
+  }
 }
 
-// cp.async (LDGSTS): global -> shared without a register round trip
-__device__ __forceinline__ void cp_async8(void* smem_dst, const void* gmem_src) {
-  const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
-  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"(d), "l"(gmem_src) : "memory");
+__device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double b) {
+  asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+      : "+d"(c0), "+d"(c1)
+      : "d"(a), "d"(b));
 }
-__device__ __forceinline__ void cp_async16_zfill(void* smem_dst, const void* gmem_src, int src_bytes) {
-  const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
-  asm volatile("cp.async.ca.shared.global [%0], [%1], 16, %2;\n" ::"r"(d), "l"(gmem_src), "r"(src_bytes) : "memory");
+
+// ---- mbarrier + TMA bulk copy -----------------------------------------------------------------------
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
 }
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
-__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;\n" ::: "memory"); }
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred P1;\n"
+      "LAB_WAIT:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+      "@P1 bra DONE;\n"
+      "bra LAB_WAIT;\n"
+      "DONE:\n"
+      "}\n" ::"r"(bar), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void tma_bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+
+// 1/d for the operand tiles: MUFU.RCP64H seed (SFU, not the FP64 pipe) + two Newton steps (4 DFMA);
+// <= 1 ulp from the IEEE quotient on the normal range, IEEE division outside it.
+__device__ __forceinline__ double fast_rcp(double d) {
+  if (!(d > 1e-290 && d < 1e290)) return 1.0 / d;
+  double r;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(d));
+  double e = fma(-d, r, 1.0);
+  r = fma(r, e, r);
+  e = fma(-d, r, 1.0);
+  return fma(r, e, r);
+}
 
 // ---- shared memory plan (per CTA; two CTAs are resident per SM) -----------------------------------
-//   WG   : 2 stages x { W[32][36], G[32][36] }                       36 864 B
-//   MR   : 3-deep ring of M tiles [32][20]                            15 360 B
-//   STG  : thread-private staging slots filled by cp.async one chunk ahead:
-//          2 factor rows x 4 samples + y, mu, omega2, v  -> [12][256] 24 576 B
-//   E    : epilogue matrix [240][33], overlays WG + MR + STG          63 360 B
-//   AUX  : per-sample sums [32][2], profile rows [8][32]
-constexpr int LK_STG_ROWS = 2;                                   // factors staged by cp.async (others load directly)
-constexpr int LK_EPT = LK_TS * LK_KC / LK_THREADS;               // elements per thread per chunk (4)
-constexpr int LK_WG_DOUBLES = 2 * 2 * LK_TS * LK_WSTRIDE;        // 4608
-constexpr int LK_MR_DOUBLES = 3 * LK_KC * LK_MSTRIDE;            // 1920
-constexpr int LK_STG_SLOTS = LK_STG_ROWS * LK_EPT + 4;           // 12
-constexpr int LK_STG_DOUBLES = LK_STG_SLOTS * LK_THREADS;        // 3072
-constexpr int LK_MAIN_DOUBLES_RAW = LK_WG_DOUBLES + LK_MR_DOUBLES + LK_STG_DOUBLES;
-constexpr int LK_EP_DOUBLES = LK_EP_COLS * LK_EP_STRIDE;
-constexpr int LK_MAIN_DOUBLES = LK_MAIN_DOUBLES_RAW > LK_EP_DOUBLES ? LK_MAIN_DOUBLES_RAW : LK_EP_DOUBLES;
-constexpr size_t LK_AUX_BYTES = LK_TS * 2 * sizeof(double) + LK_MAX_ROWS * LK_TS * sizeof(int32_t);
+//   stage s (x2) : basis panel [16][244] | W [32][20] | G [32][20]        41 472 B each
+//   E            : epilogue matrix [240][33], overlays the stages           63 360 B
+//   AUX          : per-sample sums [32][2], profile rows [8][32], 2 full + 2 empty mbarriers
+constexpr int LK_PANEL_DOUBLES = LK_KC * LK_PSTRIDE;               // 3904
+constexpr int LK_WG_DOUBLES = LK_TS * LK_WSTRIDE;                  // 640
+constexpr int LK_STAGE_DOUBLES = LK_PANEL_DOUBLES + 2 * LK_WG_DOUBLES;  // 5184
+constexpr uint32_t LK_PANEL_BYTES = LK_PANEL_DOUBLES * sizeof(double);  // 31 232
+constexpr int LK_EP_DOUBLES = LK_NCOLS * LK_EP_STRIDE;             // 7920
+constexpr int LK_MAIN_DOUBLES = LK_STAGES * LK_STAGE_DOUBLES > LK_EP_DOUBLES ? LK_STAGES * LK_STAGE_DOUBLES : LK_EP_DOUBLES;
+constexpr size_t LK_AUX_BYTES = LK_TS * 2 * sizeof(double) + LK_MAX_ROWS * LK_TS * sizeof(int32_t) + 2 * LK_STAGES * sizeof(uint64_t);
 constexpr size_t LK_SMEM_BYTES = (size_t)LK_MAIN_DOUBLES * sizeof(double) + LK_AUX_BYTES;
-constexpr int LK_NWARPS = LK_THREADS / 32;                       // 8
-constexpr int LK_MB = LK_TS / 8;                                 // DMMA row blocks per warp tile (4)
-constexpr int LK_NB = 4;                                         // DMMA column blocks per warp (8 warps x 4 >= 30)
+static_assert(LK_PANEL_BYTES % 16 == 0 && (LK_STAGE_DOUBLES * sizeof(double)) % 128 == 0, "TMA alignment");
 
 // grid = (ceil(max num_samples / 32), num_spectra), block = 256, dynamic smem = LK_SMEM_BYTES
 __global__ void __launch_bounds__(LK_THREADS, 2)
 sample_likelihood_kernel(const LikelihoodSpectrum* __restrict__ specs) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
+  extern __shared__ __align__(128) unsigned char smem_raw[];
   const LikelihoodSpectrum sp = specs[blockIdx.y];
   const int tile_s0 = blockIdx.x * LK_TS;
   if (tile_s0 >= sp.num_samples) return;
   if (sp.alive && *sp.alive == 0) return;
 
   double* s_main = reinterpret_cast<double*>(smem_raw);
-  double* s_wg = s_main;
-  double* s_mr = s_wg + LK_WG_DOUBLES;
-  double* s_stg = s_mr + LK_MR_DOUBLES;
   double* s_sums = s_main + LK_MAIN_DOUBLES;                          // [32][2] : sum r^2/d, sum log d
   int32_t* s_rows = reinterpret_cast<int32_t*>(s_sums + LK_TS * 2);   // [num_rows][32]
+  uint64_t* s_mbar = reinterpret_cast<uint64_t*>(s_rows + LK_MAX_ROWS * LK_TS);  // full[2], empty[2]
 
   const int tid = threadIdx.x;
   const int warp = tid >> 5, lane = tid & 31;
   const int n = sp.n;
-  const int nchunks = (n + LK_KC - 1) / LK_KC;
+  const int npanels = (n + LK_KC - 1) / LK_KC;
   const int num_rows = sp.num_rows;
+  const uint32_t bar_base = (uint32_t)__cvta_generic_to_shared(s_mbar);
+  auto full_bar = [&](int stage) { return bar_base + 8u * stage; };
+  auto empty_bar = [&](int stage) { return bar_base + 8u * (LK_STAGES + stage); };
 
-  // ---- profile rows of the tile's samples, zeroed sums -----------------------------------
+  // ---- profile rows of the tile's samples, barriers -------------------------------------------
   for (int e = tid; e < num_rows * LK_TS; e += LK_THREADS) {
     const int r = e / LK_TS, s = e % LK_TS;
     const int gs = tile_s0 + s;
@@ -142,198 +209,226 @@ sample_likelihood_kernel(const LikelihoodSpectrum* __restrict__ specs) {
     }
     s_rows[r * LK_TS + s] = row;
   }
-  if (tid < LK_TS * 2) s_sums[tid] = 0.0;
+  if (tid == 0) {
+#pragma unroll
+    for (int s = 0; s < LK_STAGES; ++s) {
+      mbar_init(full_bar(s), LK_WARPS + 1);  // 8 warps wrote W/G + the thread that armed the TMA byte count
+      mbar_init(empty_bar(s), LK_WARPS);     // 8 warps finished reading the stage
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
   __syncthreads();
 
-  // ---- MMA roles: warp w owns column blocks [4w, 4w+4) for all 32 samples -----------------
-  //      blocks 0..26 = Gram pairs (A = W), blocks 27..29 = projection (A = G), 30,31 do not exist
-  const int grp = lane >> 2;      // DMMA groupID
-  const int tig = lane & 3;       // DMMA threadID_in_group
-  int col_i[LK_NB], col_j[LK_NB];
+  // ---- producer role: thread -> pixel lane pl of the panel, samples sgrp and sgrp + 16 ------------
+  // (a half-warp stores 16 consecutive doubles of one W/G row: conflict-free; and reads 128
+  //  contiguous bytes of a profile row)
+  const int pl = tid & (LK_KC - 1);
+  const int sgrp = tid >> 4;  // 0..15
+  const bool two_rows = num_rows > 1;
+  bool live[LK_EPT];
+  const double* rowp0[LK_EPT];
+  const double* rowp1[LK_EPT];
 #pragma unroll
-  for (int nb = 0; nb < LK_NB; ++nb) {
-    const int blk = warp * LK_NB + nb;
-    if (blk < LK_NBLK_PAIR) {
-      col_i[nb] = c_pair_i[blk * 8 + grp];
-      col_j[nb] = c_pair_j[blk * 8 + grp];
-    } else {
-      const int j = (blk - LK_NBLK_PAIR) * 8 + grp;  // projection column (pads clamp to 0)
-      col_i[nb] = -1;
-      col_j[nb] = j < LK_K ? j : 0;
-    }
+  for (int e = 0; e < LK_EPT; ++e) {
+    const int s = sgrp + 16 * e;
+    live[e] = tile_s0 + s < sp.num_samples;
+    rowp0[e] = sp.base0 + (size_t)s_rows[s] * sp.ld;
+    rowp1[e] = two_rows ? sp.cache + (size_t)s_rows[LK_TS + s] * sp.ld : rowp0[e];
   }
-  double acc[LK_MB][LK_NB][2];
-#pragma unroll
-  for (int m = 0; m < LK_MB; ++m)
-#pragma unroll
-    for (int nb = 0; nb < LK_NB; ++nb) acc[m][nb][0] = acc[m][nb][1] = 0.0;
-
-  // ---- producer roles: warp w owns samples w, w+8, w+16, w+24; lane = pixel within the chunk ----
   double q_acc[LK_EPT], dprod[LK_EPT];
+  int esum[LK_EPT];
 #pragma unroll
-  for (int e = 0; e < LK_EPT; ++e) { q_acc[e] = 0.0; dprod[e] = 1.0; }
-  double* my_stg = s_stg + tid;  // slot k of this thread at my_stg[k * 256]
+  for (int e = 0; e < LK_EPT; ++e) { q_acc[e] = 0.0; dprod[e] = 1.0; esum[e] = 0; }
 
-  // fold the running products of d into the per-sample log-determinant sums (only this warp touches its samples)
-  auto fold_logdet = [&]() {
+  // pull the binary exponent out of the running product of d (integer pipe): keeps it in range
+  // for any panel count; non-finite / non-positive values are left alone so they still poison the log
+  auto renorm = [&]() {
 #pragma unroll
     for (int e = 0; e < LK_EPT; ++e) {
-      double l = log(dprod[e]);
-      dprod[e] = 1.0;
-#pragma unroll
-      for (int off = 16; off > 0; off >>= 1) l += __shfl_xor_sync(0xffffffffu, l, off);
-      if (lane == 0) s_sums[(warp + LK_NWARPS * e) * 2 + 1] += l;
-    }
-  };
-
-  // issue the global->shared copies of one chunk: factor rows (first two), pixel scalars, M tile
-  auto prefetch = [&](int chunk) {
-    const int p = chunk * LK_KC + lane;
-    if (p < n) {
-#pragma unroll
-      for (int e = 0; e < LK_EPT; ++e) {
-        const int s = warp + LK_NWARPS * e;
-        if (tile_s0 + s < sp.num_samples) {
-          cp_async8(my_stg + e * LK_THREADS, sp.base0 + (size_t)s_rows[s] * sp.ld + p);
-          if (num_rows > 1)
-            cp_async8(my_stg + (LK_EPT + e) * LK_THREADS, sp.cache + (size_t)s_rows[LK_TS + s] * sp.ld + p);
-        }
+      const int hi = __double2hiint(dprod[e]);
+      const int ex = (hi >> 20) & 0x7ff;
+      if (hi > 0 && ex != 0 && ex != 0x7ff) {
+        esum[e] += ex - 1023;
+        dprod[e] = __hiloint2double(hi - ((ex - 1023) << 20), __double2loint(dprod[e]));
       }
-      cp_async8(my_stg + (2 * LK_EPT + 0) * LK_THREADS, sp.y + p);
-      cp_async8(my_stg + (2 * LK_EPT + 1) * LK_THREADS, sp.mu + p);
-      cp_async8(my_stg + (2 * LK_EPT + 2) * LK_THREADS, sp.omega2 + p);
-      cp_async8(my_stg + (2 * LK_EPT + 3) * LK_THREADS, sp.v + p);
     }
-    // M tile: 640 doubles = 320 x 16 B, zero-filled beyond pixel n
-    double* Mt = s_mr + (chunk % 3) * (LK_KC * LK_MSTRIDE);
-    for (int e2 = tid; e2 < LK_KC * LK_K / 2; e2 += LK_THREADS) {
-      const int pp = chunk * LK_KC + (2 * e2) / LK_K;
-      // clamp the source so the address is always valid; src_bytes = 0 zero-fills
-      const double* src = sp.M + (size_t)(pp < n ? (chunk * LK_KC * LK_K + 2 * e2) : 0);
-      cp_async16_zfill(Mt + 2 * e2, src, pp < n ? 16 : 0);
-    }
-    cp_async_commit();
   };
 
-  // turn the staged values of one chunk into the W / G operand tiles
-  auto produce = [&](int chunk, int buf) {
-    double* Ws = s_wg + buf * (2 * LK_TS * LK_WSTRIDE);
-    double* Gs = Ws + LK_TS * LK_WSTRIDE;
-    const int p = chunk * LK_KC + lane;
+  // register buffer of the next panel's inputs (loads issued one panel ahead)
+  double f0[LK_EPT], f1[LK_EPT], yp, mup, omp, vp;
+  auto load_panel = [&](int panel) {
+    const int p = panel * LK_KC + pl;
     const bool pv = p < n;
-    double yp = 0, mup = 0, omp = 0, vp = 1;
-    if (pv) {
-      yp = my_stg[(2 * LK_EPT + 0) * LK_THREADS]; mup = my_stg[(2 * LK_EPT + 1) * LK_THREADS];
-      omp = my_stg[(2 * LK_EPT + 2) * LK_THREADS]; vp = my_stg[(2 * LK_EPT + 3) * LK_THREADS];
-    }
 #pragma unroll
     for (int e = 0; e < LK_EPT; ++e) {
-      const int s = warp + LK_NWARPS * e;
-      double w = 0.0, g = 0.0;
-      if (pv && tile_s0 + s < sp.num_samples) {
+      const bool ok = pv && live[e];
+      f0[e] = ok ? __ldg(rowp0[e] + p) : 1.0;
+      f1[e] = (ok && two_rows) ? __ldg(rowp1[e] + p) : 1.0;
+    }
+    yp = pv ? __ldg(sp.y + p) : 0.0;
+    mup = pv ? __ldg(sp.mu + p) : 0.0;
+    omp = pv ? __ldg(sp.omega2 + p) : 0.0;
+    vp = pv ? __ldg(sp.v + p) : 1.0;
+  };
+
+  // W/G tiles of `panel` into its stage; arms the TMA of the basis panel
+  auto produce = [&](int panel) {
+    const int stage = panel & (LK_STAGES - 1);
+    double* Ps = s_main + stage * LK_STAGE_DOUBLES;
+    double* Ws = Ps + LK_PANEL_DOUBLES;
+    double* Gs = Ws + LK_WG_DOUBLES;
+    const int p = panel * LK_KC + pl;
+    const bool pv = p < n;
+    double w[LK_EPT], g[LK_EPT];
+#pragma unroll
+    for (int e = 0; e < LK_EPT; ++e) {
+      const int s = sgrp + 16 * e;
+      w[e] = 0.0;
+      g[e] = 0.0;
+      if (pv && live[e]) {
         // absorption = product of the factors' profiles, left to right (dla_gp.py:370-386)
-        double a = my_stg[e * LK_THREADS];
-        if (num_rows > 1) a = a * my_stg[(LK_EPT + e) * LK_THREADS];
+        double a = f0[e];
+        if (two_rows) a = a * f1[e];
         for (int r = 2; r < num_rows; ++r) a = a * sp.cache[(size_t)s_rows[r * LK_TS + s] * sp.ld + p];
         if (sp.prod_out) sp.prod_out[(size_t)(tile_s0 + s) * sp.ld + p] = a;
         const double a2 = a * a;
         const double d = fma(omp, a2, vp);   // dla_omega2 + v
-        const double inv = 1.0 / d;
+        const double inv = fast_rcp(d);
         const double r = fma(-mup, a, yp);   // y - dla_mu
-        w = a2 * inv;
-        g = a * r * inv;
-        q_acc[e] = fma(r * r, inv, q_acc[e]);
+        const double t = r * inv;
+        w[e] = a2 * inv;
+        g[e] = a * t;
+        q_acc[e] = fma(r, t, q_acc[e]);
         dprod[e] *= d;
       }
-      Ws[s * LK_WSTRIDE + lane] = w;
-      Gs[s * LK_WSTRIDE + lane] = g;
     }
-    if ((chunk & 7) == 7) fold_logdet();  // keeps the product of d within range
+    if (panel + 1 < npanels) load_panel(panel + 1);  // in flight while this warp runs its DMMAs
+    if (panel >= LK_STAGES) mbar_wait(empty_bar(stage), ((panel / LK_STAGES) - 1) & 1);  // stage drained
+    if (tid == 0) {
+      mbar_expect_tx(full_bar(stage), LK_PANEL_BYTES);
+      tma_bulk_g2s((uint32_t)__cvta_generic_to_shared(Ps), sp.P + (size_t)panel * LK_PANEL_DOUBLES, LK_PANEL_BYTES,
+                   full_bar(stage));
+    }
+#pragma unroll
+    for (int e = 0; e < LK_EPT; ++e) {
+      Ws[(sgrp + 16 * e) * LK_WSTRIDE + pl] = w[e];
+      Gs[(sgrp + 16 * e) * LK_WSTRIDE + pl] = g[e];
+    }
+    __syncwarp();
+    if (lane == 0) mbar_arrive(full_bar(stage));
   };
 
-  // NPAIR Gram blocks followed by NPROJ projection blocks, both compile-time: the three warp
-  // classes (0..5: 4+0, 6: 3+1, 7: 0+2) get separate loop bodies - a predicated-off DMMA still
-  // costs its tensor-pipe slot.
-  auto consume_kind = [&](int chunk, int buf, auto npair_c, auto nproj_c) {
-    constexpr int NPAIR = decltype(npair_c)::value;
-    constexpr int NPROJ = decltype(nproj_c)::value;
-    const double* Ws = s_wg + buf * (2 * LK_TS * LK_WSTRIDE);
-    const double* Gs = Ws + LK_TS * LK_WSTRIDE;
-    const double* Ms = s_mr + (chunk % 3) * (LK_KC * LK_MSTRIDE);
-    const int arow = grp * LK_WSTRIDE + tig;
+  // ---- MMA role: warp (rh, cq) owns samples 16 rh .. 16 rh + 15 and 7 or 8 column blocks -----------
+  //   rh = 0 : blocks [0,8) [8,15) [15,23) [23,30)      rh = 1 : blocks [0,7) [7,15) [15,22) [22,30)
+  // Blocks >= 27 are the projection part (A = G).  Local blocks 0..3 always take A = W, local block 4
+  // and local blocks 5..7 read A through pointers (W or G), so all warps run one instruction stream
+  // with no predicated DMMA; the eighth block sits behind a warp-uniform branch.
+  const int grp = lane >> 2;      // DMMA groupID
+  const int tig = lane & 3;       // DMMA threadID_in_group
+  const int rh = warp >> 2, cq = warp & 3;
+  const int first = rh == 0 ? (cq == 0 ? 0 : cq == 1 ? 8 : cq == 2 ? 15 : 23) : (cq == 0 ? 0 : cq == 1 ? 7 : cq == 2 ? 15 : 22);
+  const bool has_eighth = ((cq + rh) & 1) == 0;
+  const bool g4 = first + 4 >= LK_NBLK_PAIR, g5 = first + 5 >= LK_NBLK_PAIR;
+  double acc[LK_MB][LK_NB_MAX][2];
+#pragma unroll
+  for (int m = 0; m < LK_MB; ++m)
+#pragma unroll
+    for (int nb = 0; nb < LK_NB_MAX; ++nb) acc[m][nb][0] = acc[m][nb][1] = 0.0;
+
+  auto consume = [&](int panel) {
+    const int stage = panel & (LK_STAGES - 1);
+    const double* Ps = s_main + stage * LK_STAGE_DOUBLES;
+    const double* Ws = Ps + LK_PANEL_DOUBLES;
+    const double* Gs = Ws + LK_WG_DOUBLES;
+    mbar_wait(full_bar(stage), (panel / LK_STAGES) & 1);  // W/G written by all warps, basis panel landed
+    const int aoff = (rh * 16 + grp) * LK_WSTRIDE + tig;
+    const double* arow = Ws + aoff;
+    const double* a4row = (g4 ? Gs : Ws) + aoff;
+    const double* a5row = (g5 ? Gs : Ws) + aoff;
+    const double* brow = Ps + tig * LK_PSTRIDE + first * 8 + grp;
 #pragma unroll
     for (int kb = 0; kb < LK_KC / 4; ++kb) {
-      const double* mrow = Ms + (kb * 4 + tig) * LK_MSTRIDE;
-      if (NPAIR > 0) {
-        double aw[LK_MB];
+      double a[LK_MB];
 #pragma unroll
-        for (int m = 0; m < LK_MB; ++m) aw[m] = Ws[arow + m * 8 * LK_WSTRIDE + kb * 4];
+      for (int m = 0; m < LK_MB; ++m) a[m] = arow[m * 8 * LK_WSTRIDE + kb * 4];
 #pragma unroll
-        for (int nb = 0; nb < NPAIR; ++nb) {
-          const double b = mrow[col_i[nb]] * mrow[col_j[nb]];
+      for (int nb = 0; nb < 4; ++nb) {
+        const double b = brow[kb * 4 * LK_PSTRIDE + nb * 8];
 #pragma unroll
-          for (int m = 0; m < LK_MB; ++m) dmma884(acc[m][nb][0], acc[m][nb][1], aw[m], b);
-        }
+        for (int m = 0; m < LK_MB; ++m) dmma884(acc[m][nb][0], acc[m][nb][1], a[m], b);
       }
-      if (NPROJ > 0) {
-        double ag[LK_MB];
 #pragma unroll
-        for (int m = 0; m < LK_MB; ++m) ag[m] = Gs[arow + m * 8 * LK_WSTRIDE + kb * 4];
+      for (int m = 0; m < LK_MB; ++m) a[m] = a4row[m * 8 * LK_WSTRIDE + kb * 4];
+      {
+        const double b = brow[kb * 4 * LK_PSTRIDE + 4 * 8];
 #pragma unroll
-        for (int nb = NPAIR; nb < NPAIR + NPROJ; ++nb) {
-          const double b = mrow[col_j[nb]];
+        for (int m = 0; m < LK_MB; ++m) dmma884(acc[m][4][0], acc[m][4][1], a[m], b);
+      }
 #pragma unroll
-          for (int m = 0; m < LK_MB; ++m) dmma884(acc[m][nb][0], acc[m][nb][1], ag[m], b);
-        }
+      for (int m = 0; m < LK_MB; ++m) a[m] = a5row[m * 8 * LK_WSTRIDE + kb * 4];
+#pragma unroll
+      for (int nb = 5; nb < 7; ++nb) {
+        const double b = brow[kb * 4 * LK_PSTRIDE + nb * 8];
+#pragma unroll
+        for (int m = 0; m < LK_MB; ++m) dmma884(acc[m][nb][0], acc[m][nb][1], a[m], b);
       }
     }
-  };
-  auto consume = [&](int chunk, int buf) {
-    using std::integral_constant;
-    if (warp < 6) consume_kind(chunk, buf, integral_constant<int, 4>(), integral_constant<int, 0>());
-    else if (warp == 6) consume_kind(chunk, buf, integral_constant<int, 3>(), integral_constant<int, 1>());
-    else consume_kind(chunk, buf, integral_constant<int, 0>(), integral_constant<int, 2>());
+    if (has_eighth) {
+#pragma unroll
+      for (int kb = 0; kb < LK_KC / 4; ++kb) {
+        const double b = brow[kb * 4 * LK_PSTRIDE + 7 * 8];
+#pragma unroll
+        for (int m = 0; m < LK_MB; ++m)
+          dmma884(acc[m][7][0], acc[m][7][1], a5row[m * 8 * LK_WSTRIDE + kb * 4], b);
+      }
+    }
+    if (panel + LK_STAGES < npanels) {  // the stage may be refilled
+      __syncwarp();
+      if (lane == 0) mbar_arrive(empty_bar(stage));
+    }
   };
 
-  // ---- main loop: chunk c+2 in flight (cp.async), chunk c+1 being produced, chunk c in the MMAs ----
-  prefetch(0);
-  cp_async_wait_all();
-  produce(0, 0);          // reads only this thread's own staging slots
-  if (nchunks > 1) prefetch(1);
-  __syncthreads();        // W/G(0) and M(0) visible to all warps
-  for (int chunk = 0; chunk < nchunks; ++chunk) {
-    const int buf = chunk & 1;
-    if (chunk + 1 < nchunks) {
-      cp_async_wait_all();             // staged values + M tile of chunk+1 have landed (issued one MMA phase ago)
-      produce(chunk + 1, buf ^ 1);
-      if (chunk + 2 < nchunks) prefetch(chunk + 2);
-    }
-    consume(chunk, buf);
-    __syncthreads();
+  // ---- main loop: every warp produces panel c+1, then runs its DMMAs on panel c --------------------
+  load_panel(0);
+  produce(0);
+  for (int panel = 0; panel < npanels; ++panel) {
+    if (panel + 1 < npanels) produce(panel + 1);
+    consume(panel);
+    if ((panel & 7) == 7) renorm();
   }
 
-  // ---- per-sample scalar sums: reduce over the 32 pixel lanes -----------------------------
-  fold_logdet();
+  // per-sample scalar sums: reduce over the 16 pixel lanes of the half-warp
+  renorm();
 #pragma unroll
   for (int e = 0; e < LK_EPT; ++e) {
     double q = q_acc[e];
+    double l = fma((double)esum[e], LK_LN2, log(dprod[e]));
 #pragma unroll
-    for (int off = 16; off > 0; off >>= 1) q += __shfl_xor_sync(0xffffffffu, q, off);
-    if (lane == 0) s_sums[(warp + LK_NWARPS * e) * 2] = q;
+    for (int off = 8; off > 0; off >>= 1) {
+      q += __shfl_xor_sync(0xffffffffu, q, off);
+      l += __shfl_xor_sync(0xffffffffu, l, off);
+    }
+    if (pl == 0) {
+      s_sums[(sgrp + 16 * e) * 2] = q;
+      s_sums[(sgrp + 16 * e) * 2 + 1] = l;
+    }
   }
+  __syncthreads();  // every panel consumed by every warp; the stages can be overlaid
 
-  // ---- accumulators -> E[col][sample] (overlays the stage buffers; all reads finished) -----
+  // ---- accumulators -> E[col][sample] -----------------------------------------------------------
   double* E = s_main;
+  {
+    const int count = has_eighth ? 8 : 7;
 #pragma unroll
-  for (int m = 0; m < LK_MB; ++m) {
-    const int s = m * 8 + grp;
+    for (int m = 0; m < LK_MB; ++m) {
+      const int s = rh * 16 + m * 8 + grp;
 #pragma unroll
-    for (int nb = 0; nb < LK_NB; ++nb) {
-      const int blk = warp * LK_NB + nb;
-      if (blk < LK_NBLK) {
-        const int col = blk * 8 + tig * 2;
-        E[col * LK_EP_STRIDE + s] = acc[m][nb][0];
-        E[(col + 1) * LK_EP_STRIDE + s] = acc[m][nb][1];
+      for (int nb = 0; nb < LK_NB_MAX; ++nb) {
+        if (nb < count) {
+          const int col = (first + nb) * 8 + tig * 2;
+          E[col * LK_EP_STRIDE + s] = acc[m][nb][0];
+          E[(col + 1) * LK_EP_STRIDE + s] = acc[m][nb][1];
+        }
       }
     }
   }
@@ -347,7 +442,7 @@ sample_likelihood_kernel(const LikelihoodSpectrum* __restrict__ specs) {
     const int t = tid & 3;
     double* Es = E + s;
     auto at = [&](int i, int j) -> double& {  // element (i,j), i >= j, i <= 20
-      const int col = (i < LK_K) ? (i * (i + 1) / 2 + j) : (216 + j);
+      const int col = (i < LK_K) ? (i * (i + 1) / 2 + j) : (LK_PROJ_COL0 + j);
       return Es[col * LK_EP_STRIDE];
     };
     double logdet_prod = 1.0, logdet = 0.0, zz = 0.0;
