@@ -23,9 +23,10 @@
 //   * warp (rh, cq) owns 16 samples x 7 or 8 of the 30 column blocks, sized [8,7,8,7] / [7,8,7,8]
 //     so that the two warps of every SM sub-partition issue 30 DMMAs per 4 pixels: no padding
 //     block, four balanced FP64 pipes;
-//   * hand-over between panels by mbarriers (full: 8 warp arrivals + the TMA byte count; empty:
-//     8 warp arrivals), split-phase, so warps drift by up to a panel instead of meeting at a
-//     CTA-wide barrier;
+//   * no CTA-wide barrier in the main loop: W/G tiles go through a 4-deep ring (mbarrier with 8 warp
+//     arrivals per stage), basis panels through a 2-deep ring whose refill is requested by the LAST
+//     warp to leave the stage (shared-memory counter), so nobody ever waits for a stage to drain and
+//     warps drift by up to a panel;
 //   * the bordered 21 x 21 Cholesky (factor, z = L^-1 c, log-det) of every sample runs in shared
 //     memory straight out of the accumulator fragments while the SM's other CTA keeps the
 //     tensor pipe busy.
@@ -48,7 +49,8 @@ constexpr int LK_PSTRIDE = LK_NCOLS + 4;         // basis row stride (244 == 4 m
 constexpr int LK_PROJ_COL0 = LK_NBLK_PAIR * 8;   // 216: first projection column
 constexpr int LK_WARPS = 8;
 constexpr int LK_THREADS = LK_WARPS * 32;        // 256
-constexpr int LK_STAGES = 2;
+constexpr int LK_PSTAGES = 2;                    // basis-panel ring (TMA)
+constexpr int LK_WSTAGES = 4;                    // W/G operand ring
 constexpr int LK_EP_STRIDE = LK_TS + 1;          // epilogue smem: [col][sample], stride 33
 constexpr int LK_MAX_ROWS = 8;                   // max absorbers multiplied per sample (max_dlas <= 8)
 constexpr int LK_MB = 2;                         // DMMA row blocks per warp (16 samples)
@@ -162,18 +164,20 @@ __device__ __forceinline__ double fast_rcp(double d) {
 }
 
 // ---- shared memory plan (per CTA; two CTAs are resident per SM) -----------------------------------
-//   stage s (x2) : basis panel [16][244] | W [32][20] | G [32][20]        41 472 B each
-//   E            : epilogue matrix [240][33], overlays the stages           63 360 B
-//   AUX          : per-sample sums [32][2], profile rows [8][32], 2 full + 2 empty mbarriers
+//   basis ring : 2 x [16][244]                                              62 464 B
+//   W/G ring   : 4 x { W [32][20] | G [32][20] }                            40 960 B
+//   E          : epilogue matrix [240][33], overlays the rings              63 360 B
+//   AUX        : per-sample sums [32][2], profile rows [8][32], mbarriers, drain counters
 constexpr int LK_PANEL_DOUBLES = LK_KC * LK_PSTRIDE;               // 3904
 constexpr int LK_WG_DOUBLES = LK_TS * LK_WSTRIDE;                  // 640
-constexpr int LK_STAGE_DOUBLES = LK_PANEL_DOUBLES + 2 * LK_WG_DOUBLES;  // 5184
 constexpr uint32_t LK_PANEL_BYTES = LK_PANEL_DOUBLES * sizeof(double);  // 31 232
+constexpr int LK_RING_DOUBLES = LK_PSTAGES * LK_PANEL_DOUBLES + LK_WSTAGES * 2 * LK_WG_DOUBLES;  // 12 928
 constexpr int LK_EP_DOUBLES = LK_NCOLS * LK_EP_STRIDE;             // 7920
-constexpr int LK_MAIN_DOUBLES = LK_STAGES * LK_STAGE_DOUBLES > LK_EP_DOUBLES ? LK_STAGES * LK_STAGE_DOUBLES : LK_EP_DOUBLES;
-constexpr size_t LK_AUX_BYTES = LK_TS * 2 * sizeof(double) + LK_MAX_ROWS * LK_TS * sizeof(int32_t) + 2 * LK_STAGES * sizeof(uint64_t);
+constexpr int LK_MAIN_DOUBLES = LK_RING_DOUBLES > LK_EP_DOUBLES ? LK_RING_DOUBLES : LK_EP_DOUBLES;
+constexpr size_t LK_AUX_BYTES = LK_TS * 2 * sizeof(double) + LK_MAX_ROWS * LK_TS * sizeof(int32_t) +
+                                (LK_PSTAGES + LK_WSTAGES) * sizeof(uint64_t) + LK_PSTAGES * sizeof(int);
 constexpr size_t LK_SMEM_BYTES = (size_t)LK_MAIN_DOUBLES * sizeof(double) + LK_AUX_BYTES;
-static_assert(LK_PANEL_BYTES % 16 == 0 && (LK_STAGE_DOUBLES * sizeof(double)) % 128 == 0, "TMA alignment");
+static_assert(LK_PANEL_BYTES % 128 == 0, "TMA alignment");
 
 // grid = (ceil(max num_samples / 32), num_spectra), block = 256, dynamic smem = LK_SMEM_BYTES
 __global__ void __launch_bounds__(LK_THREADS, 2)
@@ -187,7 +191,8 @@ sample_likelihood_kernel(const LikelihoodSpectrum* __restrict__ specs) {
   double* s_main = reinterpret_cast<double*>(smem_raw);
   double* s_sums = s_main + LK_MAIN_DOUBLES;                          // [32][2] : sum r^2/d, sum log d
   int32_t* s_rows = reinterpret_cast<int32_t*>(s_sums + LK_TS * 2);   // [num_rows][32]
-  uint64_t* s_mbar = reinterpret_cast<uint64_t*>(s_rows + LK_MAX_ROWS * LK_TS);  // full[2], empty[2]
+  uint64_t* s_mbar = reinterpret_cast<uint64_t*>(s_rows + LK_MAX_ROWS * LK_TS);  // panel[2], wg[4]
+  int* s_drain = reinterpret_cast<int*>(s_mbar + LK_PSTAGES + LK_WSTAGES);       // [2] warps done with a basis stage
 
   const int tid = threadIdx.x;
   const int warp = tid >> 5, lane = tid & 31;
@@ -195,8 +200,9 @@ sample_likelihood_kernel(const LikelihoodSpectrum* __restrict__ specs) {
   const int npanels = (n + LK_KC - 1) / LK_KC;
   const int num_rows = sp.num_rows;
   const uint32_t bar_base = (uint32_t)__cvta_generic_to_shared(s_mbar);
-  auto full_bar = [&](int stage) { return bar_base + 8u * stage; };
-  auto empty_bar = [&](int stage) { return bar_base + 8u * (LK_STAGES + stage); };
+  auto panel_bar = [&](int stage) { return bar_base + 8u * stage; };             // basis panel landed (TMA bytes)
+  auto wg_bar = [&](int stage) { return bar_base + 8u * (LK_PSTAGES + stage); };   // W/G written by the 8 warps
+  double* s_wg = s_main + LK_PSTAGES * LK_PANEL_DOUBLES;
 
   // ---- profile rows of the tile's samples, barriers -------------------------------------------
   for (int e = tid; e < num_rows * LK_TS; e += LK_THREADS) {
@@ -209,13 +215,20 @@ sample_likelihood_kernel(const LikelihoodSpectrum* __restrict__ specs) {
     }
     s_rows[r * LK_TS + s] = row;
   }
+  // basis panel `panel` -> its ring stage (one thread; completion is the stage's mbarrier)
+  auto issue_panel = [&](int panel) {
+    const int stage = panel & (LK_PSTAGES - 1);
+    mbar_expect_tx(panel_bar(stage), LK_PANEL_BYTES);
+    tma_bulk_g2s((uint32_t)__cvta_generic_to_shared(s_main + stage * LK_PANEL_DOUBLES),
+                 sp.P + (size_t)panel * LK_PANEL_DOUBLES, LK_PANEL_BYTES, panel_bar(stage));
+  };
   if (tid == 0) {
 #pragma unroll
-    for (int s = 0; s < LK_STAGES; ++s) {
-      mbar_init(full_bar(s), LK_WARPS + 1);  // 8 warps wrote W/G + the thread that armed the TMA byte count
-      mbar_init(empty_bar(s), LK_WARPS);     // 8 warps finished reading the stage
-    }
+    for (int s = 0; s < LK_PSTAGES; ++s) { mbar_init(panel_bar(s), 1); s_drain[s] = 0; }
+#pragma unroll
+    for (int s = 0; s < LK_WSTAGES; ++s) mbar_init(wg_bar(s), LK_WARPS);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    for (int c = 0; c < LK_PSTAGES && c < npanels; ++c) issue_panel(c);
   }
   __syncthreads();
 
@@ -254,28 +267,28 @@ sample_likelihood_kernel(const LikelihoodSpectrum* __restrict__ specs) {
     }
   };
 
-  // register buffer of the next panel's inputs (loads issued one panel ahead)
+  // register buffer of the next panel's inputs (loads issued one panel ahead).  The loads are
+  // unconditional on clamped addresses - a predicated load drags a dependent select behind it and
+  // the warp would sit on the DRAM latency instead of running its DMMAs; validity is applied at use.
   double f0[LK_EPT], f1[LK_EPT], yp, mup, omp, vp;
   auto load_panel = [&](int panel) {
-    const int p = panel * LK_KC + pl;
-    const bool pv = p < n;
+    const int p = min(panel * LK_KC + pl, n - 1);
 #pragma unroll
     for (int e = 0; e < LK_EPT; ++e) {
-      const bool ok = pv && live[e];
-      f0[e] = ok ? __ldg(rowp0[e] + p) : 1.0;
-      f1[e] = (ok && two_rows) ? __ldg(rowp1[e] + p) : 1.0;
+      f0[e] = __ldg(rowp0[e] + p);
+      f1[e] = __ldg(rowp1[e] + p);
     }
-    yp = pv ? __ldg(sp.y + p) : 0.0;
-    mup = pv ? __ldg(sp.mu + p) : 0.0;
-    omp = pv ? __ldg(sp.omega2 + p) : 0.0;
-    vp = pv ? __ldg(sp.v + p) : 1.0;
+    yp = __ldg(sp.y + p);
+    mup = __ldg(sp.mu + p);
+    omp = __ldg(sp.omega2 + p);
+    vp = __ldg(sp.v + p);
   };
 
-  // W/G tiles of `panel` into its stage; arms the TMA of the basis panel
+  // W/G tiles of `panel` into stage panel % 4.  No wait: a warp can only be here after the basis
+  // panel of `panel - 1` landed, which was requested after ALL warps finished panel - 3 (the previous
+  // user of this W/G stage).
   auto produce = [&](int panel) {
-    const int stage = panel & (LK_STAGES - 1);
-    double* Ps = s_main + stage * LK_STAGE_DOUBLES;
-    double* Ws = Ps + LK_PANEL_DOUBLES;
+    double* Ws = s_wg + (panel & (LK_WSTAGES - 1)) * (2 * LK_WG_DOUBLES);
     double* Gs = Ws + LK_WG_DOUBLES;
     const int p = panel * LK_KC + pl;
     const bool pv = p < n;
@@ -303,19 +316,13 @@ sample_likelihood_kernel(const LikelihoodSpectrum* __restrict__ specs) {
       }
     }
     if (panel + 1 < npanels) load_panel(panel + 1);  // in flight while this warp runs its DMMAs
-    if (panel >= LK_STAGES) mbar_wait(empty_bar(stage), ((panel / LK_STAGES) - 1) & 1);  // stage drained
-    if (tid == 0) {
-      mbar_expect_tx(full_bar(stage), LK_PANEL_BYTES);
-      tma_bulk_g2s((uint32_t)__cvta_generic_to_shared(Ps), sp.P + (size_t)panel * LK_PANEL_DOUBLES, LK_PANEL_BYTES,
-                   full_bar(stage));
-    }
 #pragma unroll
     for (int e = 0; e < LK_EPT; ++e) {
       Ws[(sgrp + 16 * e) * LK_WSTRIDE + pl] = w[e];
       Gs[(sgrp + 16 * e) * LK_WSTRIDE + pl] = g[e];
     }
     __syncwarp();
-    if (lane == 0) mbar_arrive(full_bar(stage));
+    if (lane == 0) mbar_arrive(wg_bar(panel & (LK_WSTAGES - 1)));
   };
 
   // ---- MMA role: warp (rh, cq) owns samples 16 rh .. 16 rh + 15 and 7 or 8 column blocks -----------
@@ -336,11 +343,12 @@ sample_likelihood_kernel(const LikelihoodSpectrum* __restrict__ specs) {
     for (int nb = 0; nb < LK_NB_MAX; ++nb) acc[m][nb][0] = acc[m][nb][1] = 0.0;
 
   auto consume = [&](int panel) {
-    const int stage = panel & (LK_STAGES - 1);
-    const double* Ps = s_main + stage * LK_STAGE_DOUBLES;
-    const double* Ws = Ps + LK_PANEL_DOUBLES;
+    const int pstage = panel & (LK_PSTAGES - 1), wstage = panel & (LK_WSTAGES - 1);
+    const double* Ps = s_main + pstage * LK_PANEL_DOUBLES;
+    const double* Ws = s_wg + wstage * (2 * LK_WG_DOUBLES);
     const double* Gs = Ws + LK_WG_DOUBLES;
-    mbar_wait(full_bar(stage), (panel / LK_STAGES) & 1);  // W/G written by all warps, basis panel landed
+    mbar_wait(wg_bar(wstage), (panel / LK_WSTAGES) & 1);     // W/G written by all warps
+    mbar_wait(panel_bar(pstage), (panel / LK_PSTAGES) & 1);  // basis panel landed
     const int aoff = (rh * 16 + grp) * LK_WSTRIDE + tig;
     const double* arow = Ws + aoff;
     const double* a4row = (g4 ? Gs : Ws) + aoff;
@@ -382,9 +390,13 @@ sample_likelihood_kernel(const LikelihoodSpectrum* __restrict__ specs) {
           dmma884(acc[m][7][0], acc[m][7][1], a5row[m * 8 * LK_WSTRIDE + kb * 4], b);
       }
     }
-    if (panel + LK_STAGES < npanels) {  // the stage may be refilled
+    if (panel + LK_PSTAGES < npanels) {
+      // the last warp to leave the basis stage requests the panel that reuses it: nobody waits
       __syncwarp();
-      if (lane == 0) mbar_arrive(empty_bar(stage));
+      if (lane == 0 && atomicAdd(&s_drain[pstage], 1) == LK_WARPS - 1) {
+        s_drain[pstage] = 0;
+        issue_panel(panel + LK_PSTAGES);
+      }
     }
   };
 
