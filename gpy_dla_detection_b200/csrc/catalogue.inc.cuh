@@ -77,7 +77,7 @@ struct dla_catalogue {
   // per-batch workspace
   DevBuf<uint8_t> ind_unmasked, ind;
   DevBuf<double> x, y, v, this_wl, mu, omega2, M, unmasked_wl, wl_abs, padded_wl, scratch, scalars;
-  DevBuf<int32_t> uidx;
+  DevBuf<int32_t> uidx, qmap;
   DevBuf<double> z_samples, cache, prod, raw_ll0, raw_ll, sample_ll_dla, sample_ll_sub, log_ev_dla, log_ev_sub, cdf;
   DevBuf<double> log_lik, log_priors, log_post, model_post, p_dla, p_no_dla, map_z, map_lognhi;
   DevBuf<double> basis;  // Gram basis panels of the batch's spectra
@@ -201,6 +201,7 @@ static int cat_ensure_workspace(dla_catalogue* cat) {
   DLA_CUDA(cat->omega2.ensure(B * cap));
   DLA_CUDA(cat->M.ensure(B * cap * LK_K));
   DLA_CUDA(cat->uidx.ensure(B * cap));
+  DLA_CUDA(cat->qmap.ensure(B * cap));
   DLA_CUDA(cat->unmasked_wl.ensure(B * cap));
   DLA_CUDA(cat->wl_abs.ensure(B * (cap + 2 * w)));
   DLA_CUDA(cat->padded_wl.ensure(B * (cap + 2 * w)));
@@ -348,6 +349,7 @@ extern "C" int dla_catalogue_run_staged(dla_catalogue* cat, dla_catalogue_output
       AbsorptionGrid g;
       g.wl = h_prep[b].wl_abs;
       g.uidx = h_prep[b].uidx;
+      g.qmap = cat->qmap.p + (size_t)b * cap;
       g.out = cache_b;
       g.n_in = cat->params.broadening ? nu_b[b] + 2 * w : nu_b[b];
       g.n_out = n_b[b];
@@ -483,15 +485,10 @@ extern "C" int dla_catalogue_run_staged(dla_catalogue* cat, dla_catalogue_output
     // profiles
     cudaEvent_t e_v0 = cat_event(cat, ev_i++), e_v1 = cat_event(cat, ev_i++);
     {
-      const int smem_row = (int)round_up((size_t)max_n_abs + 32, 2);
-      int warps = 8;
-      while (warps > 1 && (size_t)warps * smem_row * sizeof(double) > rt.smem_optin) warps >>= 1;
-      DLA_REQUIRE((size_t)warps * smem_row * sizeof(double) <= rt.smem_optin, "absorption grid too long for shared memory");
-      dim3 grid((2 * S + warps - 1) / warps, nb);
-      DLA_CUDA(cudaEventRecord(e_v0, rt.stream));
-      voigt_profile_kernel<<<grid, warps * 32, (size_t)warps * smem_row * sizeof(double), rt.stream>>>(
-          cat->grid_desc.p, cat->params.num_lines, cat->params.broadening, smem_row);
+      build_qmap_kernel<<<nb, 256, 0, rt.stream>>>(cat->grid_desc.p, cat->params.broadening);
       DLA_LAUNCHED();
+      DLA_CUDA(cudaEventRecord(e_v0, rt.stream));
+      if ((rc = launch_voigt_grids(cat->grid_desc.p, 2 * S, nb, cat->params.num_lines, cat->params.broadening))) return rc;
       DLA_CUDA(cudaEventRecord(e_v1, rt.stream));
     }
     // levels

@@ -71,7 +71,6 @@ static int init_device(int device) {
   DLA_CUDA(cudaMemcpyToSymbol(c_pair_i, pi, sizeof(pi)));
   DLA_CUDA(cudaMemcpyToSymbol(c_pair_j, pj, sizeof(pj)));
   DLA_CUDA(cudaFuncSetAttribute(sample_likelihood_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LK_SMEM_BYTES));
-  DLA_CUDA(cudaFuncSetAttribute(voigt_profile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rt.smem_optin));
   rt.ready = true;
   return 0;
 }
@@ -153,7 +152,7 @@ struct dla_spectrum {
   DevBuf<uint8_t> mask, ind_unmasked, ind;
   // prepared arrays
   DevBuf<double> x, y, v, this_wl, mu, omega2, M, unmasked_wl, wl_abs, padded_wl, d_scalars;
-  DevBuf<int32_t> uidx;
+  DevBuf<int32_t> uidx, qmap;
   // work buffers (grown on demand)
   DevBuf<double> cache, prod, z_dev, nhi_dev, uniforms, raw_ll, sample_ll, log_ev, cdf;
   DevBuf<int32_t> rows;
@@ -170,6 +169,19 @@ struct dla_spectrum {
 // ------------------------------------------------------------------------------------------
 // launch helpers (single spectrum = batch of one)
 // ------------------------------------------------------------------------------------------
+// profiles of `max_samples` absorbers for each of `num_spectra` grids; num_lines = 3 (the published
+// configuration) runs the fully unrolled instantiation
+static int launch_voigt_grids(const AbsorptionGrid* d_grids, int max_samples, int num_spectra, int num_lines, int broadening) {
+  Runtime& rt = runtime();
+  dim3 grid((max_samples + VG_WARPS - 1) / VG_WARPS, num_spectra);
+  if (num_lines == 3)
+    voigt_profile_kernel<3><<<grid, VG_WARPS * 32, 0, rt.stream>>>(d_grids, num_lines, broadening);
+  else
+    voigt_profile_kernel<0><<<grid, VG_WARPS * 32, 0, rt.stream>>>(d_grids, num_lines, broadening);
+  DLA_LAUNCHED();
+  return 0;
+}
+
 static int launch_voigt(dla_spectrum* sp, const double* d_z, const double* d_nhi, int num_samples, int num_lines,
                         double* d_out, int ld) {
   Runtime& rt = runtime();
@@ -184,17 +196,14 @@ static int launch_voigt(dla_spectrum* sp, const double* d_z, const double* d_nhi
   g.num_samples = num_samples;
   g.z = d_z;
   g.nhi = d_nhi;
+  const int n_u = sp->broadening ? sp->n_abs - 2 * INSTRUMENT_WIDTH : sp->n_abs;
+  DLA_CUDA(sp->qmap.ensure(std::max(n_u, 1)));
+  g.qmap = sp->qmap.p;
   DLA_CUDA(sp->grid_desc.ensure(1));
   DLA_CUDA(cudaMemcpyAsync(sp->grid_desc.p, &g, sizeof(g), cudaMemcpyHostToDevice, rt.stream));
-  const int smem_row = (int)round_up((size_t)sp->n_abs + 32, 2);
-  int warps = 8;
-  while (warps > 1 && (size_t)warps * smem_row * sizeof(double) > rt.smem_optin) warps >>= 1;
-  DLA_REQUIRE((size_t)warps * smem_row * sizeof(double) <= rt.smem_optin, "absorption grid too long for shared memory");
-  dim3 grid((num_samples + warps - 1) / warps, 1);
-  voigt_profile_kernel<<<grid, warps * 32, (size_t)warps * smem_row * sizeof(double), rt.stream>>>(
-      sp->grid_desc.p, num_lines, sp->broadening, smem_row);
+  build_qmap_kernel<<<1, 256, 0, rt.stream>>>(sp->grid_desc.p, sp->broadening);
   DLA_LAUNCHED();
-  return 0;
+  return launch_voigt_grids(sp->grid_desc.p, num_samples, 1, num_lines, sp->broadening);
 }
 
 static int ensure_cache(dla_spectrum* sp, size_t rows) {

@@ -1,11 +1,11 @@
 // voigt_kernel.cuh : Lyman-series absorption profiles on the device.
 //
 // Reference: voigt.voigt_absorption (voigt.py:251-322) and its native twin voigt.c:253-304.
-// One warp owns one (z_DLA, N_HI) sample of one spectrum: it evaluates the raw profile
-// exp(N_HI * sum_l -lc_l V_l(lambda)) on the padded wavelength grid into shared memory, then
-// applies the 7-tap instrument convolution and the pixel-mask compaction
-// (dla_gp.py:360,388) while writing the row of the profile cache, so the unbroadened
-// profile never touches HBM.
+// One warp owns one (z_DLA, N_HI) sample of one spectrum and streams over the wavelength grid in
+// 32-pixel chunks: raw profile exp(N_HI * sum_l -lc_l V_l(lambda)) per lane, a two-chunk ring in
+// shared memory (512 B per warp - the full row is never staged, so occupancy is register-limited),
+// then the 7-tap instrument convolution and the pixel-mask compaction (dla_gp.py:360,388) while
+// writing the row of the profile cache.  The unbroadened profile never touches HBM.
 #pragma once
 #include <stdint.h>
 #include "faddeeva.cuh"
@@ -22,6 +22,7 @@ __device__ __constant__ double c_instrument[2 * INSTRUMENT_WIDTH + 1] = INSTRUME
 struct AbsorptionGrid {
   const double* wl;    // n_in wavelengths the raw profile is evaluated on (padded or unmasked grid)
   const int32_t* uidx; // n_out: for each output pixel, its index in the in-range grid
+  const int32_t* qmap; // n_u: for each in-range pixel, its output index or -1 when masked (inverse of uidx)
   double* out;         // profile rows, row stride ld
   int n_in;            // n_u + 2*width (broadening) or n_u
   int n_out;           // modelled pixels n
@@ -31,10 +32,23 @@ struct AbsorptionGrid {
   const double* nhi;   // num_samples column densities
 };
 
-// raw profile value at one wavelength (voigt.py:296-307)
+// qmap = inverse of uidx; one CTA per spectrum
+__global__ void __launch_bounds__(256) build_qmap_kernel(const AbsorptionGrid* __restrict__ grids, int broadening) {
+  const AbsorptionGrid g = grids[blockIdx.x];
+  const int n_u = broadening ? g.n_in - 2 * INSTRUMENT_WIDTH : g.n_in;
+  int32_t* qmap = const_cast<int32_t*>(g.qmap);
+  for (int u = threadIdx.x; u < n_u; u += blockDim.x) qmap[u] = -1;
+  __syncthreads();
+  for (int q = threadIdx.x; q < g.n_out; q += blockDim.x) qmap[g.uidx[q]] = q;
+}
+
+// raw profile value at one wavelength (voigt.py:296-307); NL > 0: compile-time number of lines
+template <int NL>
 __device__ __forceinline__ double raw_profile_at(double lam, const double* mult, double nhi, int num_lines) {
   double total = 0.0;
-  for (int l = 0; l < num_lines; ++l) {
+  const int nl = NL > 0 ? NL : num_lines;
+#pragma unroll
+  for (int l = 0; l < nl; ++l) {
     // velocity = wavelengths * multipliers[l] - c   : two roundings, no FMA contraction
     const double vel = __dsub_rn(__dmul_rn(lam, mult[l]), LYMAN_C_CGS);
     // z = (v + i gamma) / (sqrt(2) sigma): numpy multiplies by the reciprocal of the real divisor
@@ -47,41 +61,62 @@ __device__ __forceinline__ double raw_profile_at(double lam, const double* mult,
   return exp(nhi * total);
 }
 
-// grid = (ceil(max_samples / warps_per_cta), num_spectra), block = 32 * warps_per_cta,
-// dynamic smem = warps_per_cta * smem_row doubles, smem_row >= n_in + 32
-__global__ void __launch_bounds__(256)
-voigt_profile_kernel(const AbsorptionGrid* __restrict__ grids, int num_lines, int broadening, int smem_row) {
-  extern __shared__ double s_raw[];
+constexpr int VG_WARPS = 8;  // samples per CTA
+
+// grid = (ceil(max_samples / 8), num_spectra), block = 256, static smem only
+template <int NL>
+__global__ void __launch_bounds__(VG_WARPS * 32)
+voigt_profile_kernel(const AbsorptionGrid* __restrict__ grids, int num_lines, int broadening) {
+  __shared__ double s_ring[VG_WARPS][2][32];
+  __shared__ double s_mult[VG_WARPS][32];
   const AbsorptionGrid g = grids[blockIdx.y];
-  const int warps_per_cta = blockDim.x >> 5;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int sample = blockIdx.x * warps_per_cta + warp;
+  const int sample = blockIdx.x * VG_WARPS + warp;
   if (sample >= g.num_samples) return;
-  double* raw = s_raw + (size_t)warp * smem_row;
-  double* mult = raw + (smem_row - 32);  // last 32 doubles of the warp's row hold the multipliers
+  double* mult = s_mult[warp];
 
   const double zd = g.z[sample];
   const double nhi = g.nhi[sample];
   // multipliers = c / (transition_wavelengths * (1 + z_dla)) / 1e8   (voigt.py:296)
-  if (lane < num_lines)
+  if (lane < (NL > 0 ? NL : num_lines))
     mult[lane] = __ddiv_rn(__ddiv_rn(LYMAN_C_CGS, __dmul_rn(c_tw_cm[lane], __dadd_rn(1.0, zd))), 1e8);
   __syncwarp();
 
-  for (int p = lane; p < g.n_in; p += 32) raw[p] = raw_profile_at(g.wl[p], mult, nhi, num_lines);
-  __syncwarp();
-
   double* out = g.out + (size_t)sample * g.ld;
-  if (broadening) {
-    for (int q = lane; q < g.n_out; q += 32) {
-      const int u = g.uidx[q];
-      // np.convolve(raw, profile, 'valid')[u] = sum_k raw[u+k] * profile[6-k]
-      double acc = 0.0;
-#pragma unroll
-      for (int k = 0; k <= 2 * INSTRUMENT_WIDTH; ++k) acc = fma(raw[u + k], c_instrument[2 * INSTRUMENT_WIDTH - k], acc);
-      out[q] = acc;
+  if (!broadening) {
+    for (int p = lane; p < g.n_in; p += 32) {
+      const double a = raw_profile_at<NL>(g.wl[p], mult, nhi, num_lines);
+      const int q = g.qmap[p];
+      if (q >= 0) out[q] = a;
     }
-  } else {
-    for (int q = lane; q < g.n_out; q += 32) out[q] = raw[g.uidx[q]];
+    return;
+  }
+  // np.convolve(raw, profile, 'valid')[u] = sum_k raw[u+k] * profile[6-k], u < n_u = n_in - 6
+  const int n_u = g.n_in - 2 * INSTRUMENT_WIDTH;
+  const int nchunks = (g.n_in + 31) >> 5;
+  double (*ring)[32] = s_ring[warp];
+  for (int j = 0; j <= nchunks; ++j) {
+    if (j < nchunks) {
+      const int p = (j << 5) + lane;
+      ring[j & 1][lane] = p < g.n_in ? raw_profile_at<NL>(g.wl[p], mult, nhi, num_lines) : 0.0;
+    }
+    __syncwarp();
+    if (j >= 1) {
+      const int u = ((j - 1) << 5) + lane;
+      if (u < n_u) {
+        const int q = g.qmap[u];
+        if (q >= 0) {
+          double acc = 0.0;
+#pragma unroll
+          for (int k = 0; k <= 2 * INSTRUMENT_WIDTH; ++k) {
+            const int t = lane + k;  // element u + k lives in chunk j-1 (t < 32) or chunk j
+            acc = fma(ring[(j - 1 + (t >> 5)) & 1][t & 31], c_instrument[2 * INSTRUMENT_WIDTH - k], acc);
+          }
+          out[q] = acc;
+        }
+      }
+    }
+    __syncwarp();  // chunk j-1 is overwritten by chunk j+1 in the next iteration
   }
   // the pad columns [n_out, ld) are never read as data (the likelihood kernel masks p >= n)
 }
