@@ -64,10 +64,22 @@ DLA_HD double dla_wing_rcp(double x2) {
 #endif
 }
 
+// Far-wing coefficients: on the device they sit in the constant bank, where a DFMA reads them as a
+// direct operand (as literals each one costs two uniform-register moves per use).
+#if defined(__CUDACC__)
+__device__ __constant__ double c_fadd_f1[FADD_F1_DEG + 1] = FADD_F1_COEF;
+__device__ __constant__ double c_fadd_f3[FADD_F3_DEG + 1] = FADD_F3_COEF;
+#endif
+
 // Far wing, |x| >= 64, given t = 1/x^2 : returns Re w.
 DLA_HD double dla_faddeeva_far(double t, double y, double y2) {
+#if defined(__CUDA_ARCH__)
+  const double* f1 = c_fadd_f1;
+  const double* f3 = c_fadd_f3;
+#else
   const double f1[FADD_F1_DEG + 1] = FADD_F1_COEF;
   const double f3[FADD_F3_DEG + 1] = FADD_F3_COEF;
+#endif
   double a1 = f1[0];
 #pragma unroll
   for (int i = 1; i <= FADD_F1_DEG; ++i) a1 = fma(a1, t, f1[i]);

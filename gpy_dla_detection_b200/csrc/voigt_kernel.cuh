@@ -42,16 +42,45 @@ __global__ void __launch_bounds__(256) build_qmap_kernel(const AbsorptionGrid* _
   for (int q = threadIdx.x; q < g.n_out; q += blockDim.x) qmap[g.uidx[q]] = q;
 }
 
-// raw profile value at one wavelength (voigt.py:296-307); NL > 0: compile-time number of lines
+// raw profile value at one wavelength (voigt.py:296-307); NL > 0: compile-time number of lines.
+// Must be called by all 32 lanes (warp vote): when every lane is in the far wing (|x| >= 64) of
+// every line - more than 9 chunks in 10 - the lines are evaluated in straight-line code; the
+// arithmetic is the same sequence of operations as the general path, so a value does not depend on
+// which path produced it.
 template <int NL>
 __device__ __forceinline__ double raw_profile_at(double lam, const double* mult, double nhi, int num_lines) {
   double total = 0.0;
   const int nl = NL > 0 ? NL : num_lines;
+  if (NL > 0) {
+    double x[NL > 0 ? NL : 1];
+    bool far = true;
 #pragma unroll
+    for (int l = 0; l < NL; ++l) {
+      // velocity = wavelengths * multipliers[l] - c   : two roundings, no FMA contraction
+      const double vel = __dsub_rn(__dmul_rn(lam, mult[l]), LYMAN_C_CGS);
+      // z = (v + i gamma) / (sqrt(2) sigma): numpy multiplies by the reciprocal of the real divisor
+      x[l] = __dmul_rn(vel, LYMAN_INV_SQRT2_SIGMA);
+      far = far && (fabs(x[l]) >= 64.0);
+    }
+    if (__all_sync(0xffffffffu, far)) {
+#pragma unroll
+      for (int l = 0; l < NL; ++l) {
+        const double y = c_damping_y[l];
+        const double ax = fabs(x[l]);
+        const double h = dla_faddeeva_far(dla_wing_rcp(ax * ax), y, y * y);
+        total += c_coef[l] * h;  // finite by construction: nansum has nothing to skip
+      }
+      return exp(nhi * total);
+    }
+#pragma unroll
+    for (int l = 0; l < NL; ++l) {
+      const double term = c_coef[l] * dla_faddeeva_re(x[l], c_damping_y[l]);
+      if (!isnan(term)) total += term;  // np.nansum
+    }
+    return exp(nhi * total);
+  }
   for (int l = 0; l < nl; ++l) {
-    // velocity = wavelengths * multipliers[l] - c   : two roundings, no FMA contraction
     const double vel = __dsub_rn(__dmul_rn(lam, mult[l]), LYMAN_C_CGS);
-    // z = (v + i gamma) / (sqrt(2) sigma): numpy multiplies by the reciprocal of the real divisor
     const double x = __dmul_rn(vel, LYMAN_INV_SQRT2_SIGMA);
     const double h = dla_faddeeva_re(x, c_damping_y[l]);
     // -leading_constants[l] * (Re w / (sqrt(2 pi) sigma)), folded into one constant (<= 1 ulp apart)
@@ -84,9 +113,10 @@ voigt_profile_kernel(const AbsorptionGrid* __restrict__ grids, int num_lines, in
 
   double* out = g.out + (size_t)sample * g.ld;
   if (!broadening) {
-    for (int p = lane; p < g.n_in; p += 32) {
-      const double a = raw_profile_at<NL>(g.wl[p], mult, nhi, num_lines);
-      const int q = g.qmap[p];
+    for (int p0 = 0; p0 < g.n_in; p0 += 32) {
+      const int p = p0 + lane;
+      const double a = raw_profile_at<NL>(g.wl[min(p, g.n_in - 1)], mult, nhi, num_lines);
+      const int q = p < g.n_in ? g.qmap[p] : -1;
       if (q >= 0) out[q] = a;
     }
     return;
@@ -98,7 +128,7 @@ voigt_profile_kernel(const AbsorptionGrid* __restrict__ grids, int num_lines, in
   for (int j = 0; j <= nchunks; ++j) {
     if (j < nchunks) {
       const int p = (j << 5) + lane;
-      ring[j & 1][lane] = p < g.n_in ? raw_profile_at<NL>(g.wl[p], mult, nhi, num_lines) : 0.0;
+      ring[j & 1][lane] = raw_profile_at<NL>(g.wl[min(p, g.n_in - 1)], mult, nhi, num_lines);  // tail lanes: unused copies
     }
     __syncwarp();
     if (j >= 1) {
