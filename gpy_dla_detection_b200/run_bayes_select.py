@@ -51,7 +51,8 @@ def log_priors_for(prior, z_qsos: np.ndarray, max_dlas: int, Z_lls: float, Z_dla
         for q in range(Q):
             counts[q] = prior.less_ind(z_qsos[q])
     out = np.full((Q, 2 + max_dlas), np.nan)
-    ratio = counts[:, 0] / counts[:, 1]
+    with np.errstate(divide="ignore", invalid="ignore"):
+        ratio = counts[:, 0] / counts[:, 1]  # 0 / 0 for a quasar below every catalogue entry -> NaN priors
     p = ratio[:, None] ** np.arange(1, max_dlas + 1)[None, :]
     for i in range(max_dlas - 1):
         p[:, i] = p[:, i] - p[:, i + 1]

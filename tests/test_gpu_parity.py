@@ -460,3 +460,58 @@ def test_kernels_actually_launch(gpu):
     dfma, dmma = ctypes.c_double(), ctypes.c_double()
     gpu.check(lib.dla_measure_fp64_peaks(ctypes.byref(dfma), ctypes.byref(dmma)))
     assert 5.0 < dfma.value < 80.0 and 5.0 < dmma.value < 80.0  # TFLOP/s, B200 FP64
+
+
+# ---- BASELINE.json configs[3]: full Lyman series (31 lines), 30 000 samples, broadening -----------------
+def test_config4_full_lyman_series_30k_samples(gpu, O):
+    """
+    num_lines = 31, S = 30 000, max_dlas = 4 on one spectrum.  The full oracle would need 2e9 wofz calls,
+    so parity is checked (a) on a random subset of the 120 000 sample likelihoods, re-evaluated one by one
+    by the oracle's restatement of sample_log_likelihood_k_dlas with the absorber chains the GPU drew, and
+    (b) through the size-independent identities of the level loop.
+    """
+    from gpy_dla_detection_b200 import synthetic
+
+    S, md, nl = 30000, 4, 31
+    st = H.Setup(S, nl)
+    z_qso = 3.4
+    spec = synthetic.make_spectrum(st.model, z_qso, seed=404)
+    proc = st.catalogue(md, True, batch_spectra=1)
+    out = proc.process(*proc.pack([spec]), np.array([z_qso]), keep_samples=True)
+    assert out["status"][0] == 0
+    ll = out["sample_log_likelihoods_dla"][0]          # (S, 4)
+    inds = out["base_sample_inds"][0].T                # (3, S)
+    assert inds.min() >= 0 and inds.max() < S
+    prep = O.prepare_spectrum(st.model, spec[0] / (1 + z_qso), spec[1], spec[2], spec[3], z_qso)
+    zs = O.sample_z_dlas(st.dla["offset_samples"], prep["this_wavelengths"], z_qso)
+    nhi = st.dla["nhi_samples"]
+    rng = np.random.default_rng(1)
+    for level in range(md):
+        finite = np.flatnonzero(np.isfinite(ll[:, level]))
+        for i in rng.choice(finite, size=6, replace=False):
+            chain = np.concatenate([[i], inds[:level, i]]).astype(int)
+            ref = O.sample_log_likelihood_k_dlas(prep, zs[chain], nhi[chain], nl, True) - np.log(S)
+            assert abs(ll[i, level] - ref) < LL_RTOL * max(abs(ref), 1.0), (level, i)
+    # subDLA column against the oracle on a subset
+    zs_sub = O.sample_z_dlas(st.sub["offset_samples"], prep["this_wavelengths"], z_qso)
+    for i in rng.choice(S, size=6, replace=False):
+        ref = O.sample_log_likelihood_k_dlas(prep, zs_sub[[i]], st.sub["nhi_samples"][[i]], nl, True) - np.log(S)
+        assert abs(out["sample_log_likelihoods_lls"][0][i] - ref) < LL_RTOL * max(abs(ref), 1.0)
+    # level identities (dla_gp.py:164-190): separation mask, log-mean-exp evidences
+    sep = st.params.kms_to_z(3000.0)
+    for level in range(1, md):
+        allz = np.concatenate([zs[None, :], zs[inds[:level]]], axis=0)
+        too_close = np.any(np.diff(np.sort(allz, axis=0), axis=0) < sep, axis=0)
+        assert np.array_equal(np.isnan(ll[:, level]), too_close)
+    for level in range(md):
+        col = ll[:, level]
+        mx = np.nanmax(col)
+        ev = mx + np.log(np.nanmean(np.exp(col - mx))) - level * np.log(S)
+        assert abs(out["log_likelihoods"][0][2 + level] - ev) < EV_ATOL
+    # resampling reproduces NumPy's choice on the GPU's own weights (bit-exact)
+    U = np.random.RandomState(0).random_sample((md - 1, S))
+    for level in range(md - 1):
+        col = ll[:, level]
+        W = np.exp(col - np.nanmax(col))
+        W[np.isnan(W)] = 0.0
+        assert np.array_equal(inds[level], O.resample_indices(W, U[level]))
