@@ -254,3 +254,60 @@ def make_spectrum(
     pixel_mask = ivar0 | bright
 
     return wavelengths, flux, noise_variance, pixel_mask
+
+
+# ----------------------------------------------------------------------------------------
+# zQSO estimation (ZGP, BASELINE.json configs[4]): learned model over 910-3000 A and spectra
+# that extend redwards of Ly-alpha with the usual broad emission lines
+# ----------------------------------------------------------------------------------------
+_EMISSION_LINES = (  # (rest wavelength, width, height): Ly-b/OVI, Ly-a, NV, SiIV, CIV, CIII], MgII
+    (1033.0, 8.0, 0.35), (1215.67, 10.0, 2.2), (1240.0, 8.0, 0.5), (1398.0, 12.0, 0.35),
+    (1549.0, 14.0, 1.1), (1909.0, 18.0, 0.6), (2799.0, 22.0, 0.5),
+)
+
+
+def make_zqso_model(seed: int = 0, k: int = 20) -> Dict[str, np.ndarray]:
+    """Synthetic stand-in for learned_zqso_only_model_*.mat (zqso_gp.py:283-319): grid 910:0.25:3000."""
+    rng = np.random.default_rng(seed + 1000)
+    rest_wavelengths = 910.0 + 0.25 * np.arange(8361)
+    mu = 0.9 * (rest_wavelengths / 1216.0) ** -1.2
+    for center, width, height in _EMISSION_LINES:
+        mu = mu + height * np.exp(-0.5 * ((rest_wavelengths - center) / width) ** 2)
+    mu = np.where(rest_wavelengths < 1216.0, mu * (0.75 + 0.25 * (rest_wavelengths - 910.0) / 306.0), mu)
+    N = rest_wavelengths.shape[0]
+    kern_x = np.arange(-160, 161)
+    kern = np.exp(-0.5 * (kern_x / 40.0) ** 2)
+    kern /= np.sqrt(np.sum(kern**2))
+    M = np.empty((N, k))
+    for j in range(k):
+        white = rng.standard_normal(N + kern_x.shape[0] - 1)
+        M[:, j] = np.convolve(white, kern, "valid") * 0.15 * (0.88**j)
+    return dict(
+        rest_wavelengths=rest_wavelengths, mu=mu, M=np.ascontiguousarray(M),
+        bluewards_mu=0.62, redwards_mu=0.21, bluewards_sigma=0.31, redwards_sigma=0.17,
+    )
+
+
+def make_zqso_spectrum(model: Dict[str, np.ndarray], z_qso: float, seed: int, num_pixels: int = 4650):
+    """BOSS-like spectrum drawn from the zQSO model at redshift z_qso (no absorbers)."""
+    rng = np.random.default_rng(seed + 5000)
+    loglam = 3.5523 + 1e-4 * np.arange(num_pixels)
+    wavelengths = 10.0**loglam
+    rest = wavelengths / (1 + z_qso)
+    rw = model["rest_wavelengths"]
+    inside = (rest >= rw[0]) & (rest <= rw[-1])
+    clean = np.where(rest < rw[0], model["bluewards_mu"], model["redwards_mu"]).astype(np.float64)
+    clean[inside] = np.interp(rest[inside], rw, model["mu"])
+    xi = rng.standard_normal(model["M"].shape[1])
+    for j in range(model["M"].shape[1]):
+        clean[inside] += np.interp(rest[inside], rw, model["M"][:, j]) * xi[j]
+    sigma_pix = np.exp(rng.normal(np.log(0.2), 0.3, size=num_pixels)) * rng.uniform(0.5, 1.5)
+    normaliser = np.exp(rng.normal(np.log(3.0), 0.5))
+    flux = (clean + sigma_pix * rng.standard_normal(num_pixels)) * normaliser
+    noise_variance = (sigma_pix * normaliser) ** 2
+    ivar0 = rng.random(num_pixels) < 0.012
+    bright = rng.random(num_pixels) < 0.004
+    with np.errstate(divide="ignore"):
+        noise_variance = np.where(ivar0, np.inf, noise_variance)
+    flux = np.where(ivar0, 0.0, flux)
+    return wavelengths, flux, noise_variance, ivar0 | bright

@@ -144,11 +144,66 @@ def golden_full():
     print("full: reference time %.1f s" % out["reference_seconds"], "p_dla", out["p_dla"])
 
 
+def golden_zqso():
+    """ZGP (zqso_gp.py): inference_z_qso over z samples, set_data attributes and evidence at single redshifts."""
+    from gpy_dla_detection.zqso_gp import ZGP as RZGP
+    from gpy_dla_detection.zqso_set_parameters import ZParameters as RZParameters
+    from gpy_dla_detection.zqso_samples import ZSamples as RZSamples
+
+    model = synthetic.make_zqso_model(0)
+
+    def build(num):
+        rp = RZParameters(num_zqso_samples=num)
+        gp = RZGP(rp, RZSamples(rp), model["rest_wavelengths"], model["mu"], model["M"], model["bluewards_mu"],
+                  model["redwards_mu"], model["bluewards_sigma"], model["redwards_sigma"])
+        return gp
+
+    out = {}
+    cases = [(2.3, 11), (3.4, 12), (4.9, 13)]
+    out["cases"] = np.array(cases, dtype=np.float64)
+    for c, (z_true, seed) in enumerate(cases):
+        wl, fl, nv, pm = synthetic.make_zqso_spectrum(model, z_true, seed=seed)
+        gp = build(96)
+        gp.inference_z_qso(wl, fl, nv, pm)
+        out["ll_%d" % c] = gp.sample_log_likelihoods
+        out["z_map_%d" % c] = gp.z_map
+        # a narrower prior volume around the truth (other arguments of inference_z_qso)
+        gp.inference_z_qso(wl, fl, nv, pm, z_qso_min=z_true - 0.05, z_qso_max=z_true + 0.05)
+        out["ll_narrow_%d" % c] = gp.sample_log_likelihoods
+        out["z_map_narrow_%d" % c] = gp.z_map
+        # attributes after set_data at one redshift + the three parts of the evidence
+        gp.set_data(wl, fl, nv, pm, z_qso=z_true + 0.013, normalize=True, build_model=True)
+        for k in ("x", "y", "v", "this_wavelengths", "this_mu", "this_M", "y_bw", "v_bw", "y_rw", "v_rw", "ind"):
+            out["%s_%d" % (k, c)] = getattr(gp, k)
+        out["evidence_%d" % c] = gp.log_model_evidence()
+    # log_mvnpdf_iid known answers (zqso_gp.py:252-278)
+    rng = np.random.default_rng(0)
+    y, mu, d = rng.standard_normal(50), rng.standard_normal(50), 0.1 + rng.random(50)
+    out["iid_y"], out["iid_mu"], out["iid_d"] = y, mu, d
+    out["iid_value"] = RZGP.log_mvnpdf_iid(y, mu, d)
+    np.savez_compressed(os.path.join(HERE, "zqso_golden.npz"), **out)
+    print("zqso_golden.npz written")
+
+    # the full published size: 10 000 z samples on one spectrum
+    wl, fl, nv, pm = synthetic.make_zqso_spectrum(model, 2.75, seed=21)
+    gp = build(10000)
+    t0 = time.time()
+    gp.inference_z_qso(wl, fl, nv, pm)
+    dt = time.time() - t0
+    np.savez_compressed(os.path.join(HERE, "zqso_full_S10000.npz"), z_true=2.75, seed=21,
+                        sample_log_likelihoods=gp.sample_log_likelihoods, z_map=gp.z_map, reference_seconds=dt)
+    print("zqso_full_S10000.npz written, reference time %.1f s, z_map %.4f" % (dt, gp.z_map))
+
+
 if __name__ == "__main__":
+    if "--only-zqso" in sys.argv:
+        golden_zqso()
+        sys.exit(0)
     if "--only-voigt" in sys.argv:
         golden_voigt()
         sys.exit(0)
     golden_voigt()
     golden_spectra()
+    golden_zqso()
     if "--no-full" not in sys.argv:
         golden_full()
