@@ -37,6 +37,15 @@ class DLAParamsStruct(ctypes.Structure):
     ]
 
 
+class ZqsoParamsStruct(ctypes.Structure):
+    _fields_ = [
+        ("min_lambda", c_double),
+        ("max_lambda", c_double),
+        ("normalization_min_lambda", c_double),
+        ("normalization_max_lambda", c_double),
+    ]
+
+
 class CatalogueConfigStruct(ctypes.Structure):
     _fields_ = [
         ("num_dla_samples", c_int),
@@ -119,6 +128,20 @@ SIGNATURES = {
         c_int,
         [c_void_p, _dp, _dp, _dp, POINTER(c_longlong), _dp],
     ),
+    "dla_zqso_model_create": (
+        c_int,
+        [_dp, _dp, _dp, c_int, c_int, c_double, c_double, c_double, c_double, POINTER(c_void_p)],
+    ),
+    "dla_zqso_model_destroy": (c_int, [c_void_p]),
+    "dla_zqso_inference": (
+        c_int,
+        [c_void_p, POINTER(ZqsoParamsStruct), c_int, POINTER(c_int64), _dp, _dp, _dp, _bp, _dp, c_int, _dp, _dp, _ip],
+    ),
+    "dla_zqso_set_data": (
+        c_int,
+        [c_void_p, POINTER(ZqsoParamsStruct), _dp, _dp, _dp, _bp, c_int, c_double, _dp, _dp, _dp, _dp, _dp, _bp, _bp, _dp],
+    ),
+    "dla_log_mvnpdf_iid": (c_int, [_dp, _dp, _dp, c_int, _dp]),
 }
 
 _lib = None

@@ -16,6 +16,7 @@
 #include "likelihood_kernel.cuh"
 #include "prep_kernel.cuh"
 #include "voigt_kernel.cuh"
+#include "zqso_kernel.cuh"
 
 namespace dla {
 
@@ -900,3 +901,4 @@ extern "C" int dla_resample_indices(const double* W, const double* uniforms, int
 }
 
 #include "catalogue.inc.cuh"
+#include "zqso.inc.cuh"

@@ -1,0 +1,462 @@
+// zqso_kernel.cuh : quasar-redshift estimation, ZGP (BASELINE.json configs[4]).
+//
+// Reference: ZGP.inference_z_qso (zqso_gp.py:214-250) loops over 10 000 candidate redshifts and for
+// each one runs set_data (:92-182: observed-frame window, nanmedian normalisation over rest
+// 1176-1256 A, bluewards / redwards splits, mask + range filter), get_interp (:66-90: linear
+// interpolation of mu and the 20 columns of M at x = lambda / (1 + z)) and log_model_evidence
+// (:184-212: low-rank Gaussian inside the window + two i.i.d. Gaussians outside).
+//
+// Unlike the DLA path the basis changes with the sample (M is re-interpolated at every z), so there
+// is no shared Gram basis: ONE WARP OWNS ONE (spectrum, z) SAMPLE.  The bordered matrix
+//     [[B - I, c], [c', q]] = sum_p (1/v_p) mt_p mt_p' ,   mt_p = [m_p (20) ; r_p ; 0 0 0]  (24)
+// is accumulated on the FP64 tensor path as the 6 lower 8x8 blocks of a 24 x 24 product: each lane
+// interpolates exactly the three entries of mt it needs for its fragment (no redundancy across the
+// warp: 96 values per 4 pixels = 24 per pixel), scales them by 1/v for the A operand and issues
+// 6 DMMAs per 4 pixels.  Per-pixel scalars (x, grid index, normalised flux, 1/v, residual) are
+// computed once by the lane that owns the pixel of a 32-pixel chunk and broadcast by shuffles.
+// Masked and out-of-range pixels stay in the stream with weight 0, so nothing is compacted.
+// The Cholesky of the bordered matrix, the i.i.d. sums and the median (bitonic sort of the <= 512
+// pixels of the normalisation window) all run inside the warp.
+#pragma once
+#include <math.h>
+#include <stdint.h>
+
+namespace dla {
+
+constexpr int ZQ_K = 20;           // rank of the learned covariance
+constexpr int ZQ_STRIDE = 24;      // padded row stride of the M / slope tables (3 DMMA column blocks)
+constexpr int ZQ_WARPS = 8;        // samples per CTA
+constexpr int ZQ_TDIM = 24;        // bordered matrix is 21 x 21 inside 24 x 24
+constexpr int ZQ_TSTRIDE = 25;
+constexpr double ZQ_LOG_2PI = 1.83787706640934534;  // zqso_gp.py:263
+constexpr double ZQ_LN2 = 0.693147180559945309417232121458;
+
+struct ZqsoModelDev {
+  const double* rest;       // n_rest grid
+  const double* mu;         // n_rest
+  const double* mu_slope;   // n_rest - 1 : (mu[i+1] - mu[i]) / (rest[i+1] - rest[i])
+  const double* M;          // n_rest x 24 (columns >= 20 are zero)
+  const double* M_slope;    // (n_rest - 1) x 24
+  int n_rest;
+  int uniform;              // rest[i] == rest[0] + i * dl exactly
+  double rest0, inv_dl;
+  double bluewards_mu, redwards_mu, bluewards_var, redwards_var;  // var = sigma^2
+};
+
+struct ZqsoParamsDev {
+  double min_lambda, max_lambda, norm_min_lambda, norm_max_lambda;
+};
+
+struct ZqsoSpectrum {
+  const double* X;      // observed wavelengths, strictly increasing
+  const double* Y;      // flux
+  const double* V;      // noise variance
+  const uint8_t* mask;  // 1 = bad pixel
+  int n_raw;
+};
+
+// slope tables (scipy interp1d: slope = (y_hi - y_lo) / (x_hi - x_lo), formed once per model)
+__global__ void zqso_slopes_kernel(const double* rest, const double* mu, const double* M /* n x k */, int n_rest, int k,
+                                   double* mu_slope, double* Mp /* n x 24 */, double* Ms /* (n-1) x 24 */) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_rest) return;
+  for (int j = 0; j < ZQ_STRIDE; ++j) Mp[(size_t)i * ZQ_STRIDE + j] = j < k ? M[(size_t)i * k + j] : 0.0;
+  if (i + 1 < n_rest) {
+    const double dx = __dsub_rn(rest[i + 1], rest[i]);
+    mu_slope[i] = __ddiv_rn(__dsub_rn(mu[i + 1], mu[i]), dx);
+    for (int j = 0; j < ZQ_STRIDE; ++j)
+      Ms[(size_t)i * ZQ_STRIDE + j] = j < k ? __ddiv_rn(__dsub_rn(M[(size_t)(i + 1) * k + j], M[(size_t)i * k + j]), dx) : 0.0;
+  }
+}
+
+// index lo of the interpolation interval for x: scipy interp1d = searchsorted(rest, x, 'left') clipped to
+// [1, n-1], minus one
+__device__ __forceinline__ int zqso_interval(const ZqsoModelDev& m, double x) {
+  int hi;
+  if (m.uniform) {
+    hi = (int)ceil((x - m.rest0) * m.inv_dl);
+    hi = max(1, min(hi, m.n_rest - 1));
+    while (hi > 1 && m.rest[hi - 1] >= x) --hi;
+    while (hi < m.n_rest - 1 && m.rest[hi] < x) ++hi;
+  } else {
+    int a = 0, b = m.n_rest;  // first index with rest[idx] >= x
+    while (a < b) {
+      const int c = (a + b) >> 1;
+      if (m.rest[c] < x) a = c + 1; else b = c;
+    }
+    hi = max(1, min(a, m.n_rest - 1));
+  }
+  return hi - 1;
+}
+
+__device__ __forceinline__ double zq_rcp(double d) {  // see likelihood_kernel.cuh : fast_rcp
+  double r0;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r0) : "d"(d));
+  double e = fma(-d, r0, 1.0);
+  double r = fma(r0, e, r0);
+  e = fma(-d, r, 1.0);
+  r = fma(r, e, r);
+  return (d > 1e-290 && d < 1e290) ? r : 1.0 / d;
+}
+
+// running product with the binary exponent pulled out (sum of logs with one log at the end)
+struct LogProd {
+  double prod = 1.0;
+  int esum = 0;
+  __device__ __forceinline__ void mul(double d) { prod *= d; }
+  __device__ __forceinline__ void renorm() {
+    const int hi = __double2hiint(prod);
+    const int ex = (hi >> 20) & 0x7ff;
+    if (hi > 0 && ex != 0 && ex != 0x7ff) {
+      esum += ex - 1023;
+      prod = __hiloint2double(hi - ((ex - 1023) << 20), __double2loint(prod));
+    }
+  }
+  __device__ __forceinline__ double value() { renorm(); return fma((double)esum, ZQ_LN2, log(prod)); }
+};
+
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
+  return v;
+}
+
+__device__ __forceinline__ void zq_dmma(double& c0, double& c1, double a, double b) {
+  asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+      : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
+}
+
+// first index in [a, b) with X[idx] > t (strict = true) or X[idx] >= t (strict = false)
+__device__ __forceinline__ int zq_bound(const double* X, int a, int b, double t, bool strict) {
+  while (a < b) {
+    const int c = (a + b) >> 1;
+    const bool go_right = strict ? (X[c] <= t) : (X[c] < t);
+    if (go_right) a = c + 1; else b = c;
+  }
+  return a;
+}
+// same on x = X / opz (monotone in the index), with the reference's own division
+__device__ __forceinline__ int zq_bound_rest(const double* X, double opz, int a, int b, double t, bool strict) {
+  while (a < b) {
+    const int c = (a + b) >> 1;
+    const double x = __ddiv_rn(X[c], opz);
+    const bool go_right = strict ? (x <= t) : (x < t);
+    if (go_right) a = c + 1; else b = c;
+  }
+  return a;
+}
+
+// grid = (ceil(S / 8), num_spectra), block = 256, dynamic smem = 8 * per_warp doubles,
+// per_warp = max(norm_cap, 24 * 25); norm_cap = power of two >= pixels in any normalisation window
+__global__ void __launch_bounds__(ZQ_WARPS * 32)
+zqso_likelihood_kernel(const ZqsoSpectrum* __restrict__ spectra, const double* __restrict__ z_samples, int S,
+                       ZqsoModelDev model, ZqsoParamsDev prm, int norm_cap, int per_warp,
+                       double* __restrict__ out /* [num_spectra][S] */) {
+  extern __shared__ double zq_smem[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int s = blockIdx.x * ZQ_WARPS + warp;
+  if (s >= S) return;
+  const ZqsoSpectrum sp = spectra[blockIdx.y];
+  double* buf = zq_smem + (size_t)warp * per_warp;
+  const double* X = sp.X;
+  const int n_raw = sp.n_raw;
+  const double z = z_samples[s];
+  const double opz = __dadd_rn(1.0, z);
+  double* out_ll = out + (size_t)blockIdx.y * S + s;
+
+  // ---- observed-frame window (zqso_gp.py:123-136): strict inequalities on both sides ------------
+  const double max_pos = __dmul_rn(prm.max_lambda, opz), min_pos = __dmul_rn(prm.min_lambda, opz);
+  const double max_obs = fmin(max_pos, X[n_raw - 1]), min_obs = fmax(min_pos, X[0]);
+  const int lo = zq_bound(X, 0, n_raw, min_obs, true);          // first X > min_obs
+  const int hi_end = zq_bound(X, 0, n_raw, max_obs, false);     // first X >= max_obs : window = [lo, hi_end)
+  const int bw_end = zq_bound(X, 0, n_raw, min_obs, false);     // X < min_obs  <=> index < bw_end
+  const int rw_begin = zq_bound(X, 0, n_raw, max_obs, true);    // X > max_obs  <=> index >= rw_begin
+
+  // ---- flux normalisation: nanmedian of the window pixels with rest 1176..1256 (mask ignored, :142-148)
+  double med;
+  {
+    const int nlo = zq_bound_rest(X, opz, lo, max(hi_end, lo), prm.norm_min_lambda, false);  // first x >= min
+    const int nhi = zq_bound_rest(X, opz, lo, max(hi_end, lo), prm.norm_max_lambda, true);   // first x > max
+    const double inf = __longlong_as_double(0x7ff0000000000000LL);
+    int count = 0;
+    for (int i = lane; i < norm_cap; i += 32) {
+      const int p = nlo + i;
+      double val = inf;
+      if (p < nhi) {
+        const double yv = sp.Y[p];
+        if (!isnan(yv)) { val = yv; ++count; }
+      }
+      buf[i] = val;
+    }
+    count = (int)(warp_sum((double)count) + 0.5);
+    __syncwarp();
+    // bitonic sort, ascending (+inf pads and NaNs-as-inf go to the end; a genuine +inf flux sorts there too)
+    for (int k = 2; k <= norm_cap; k <<= 1) {
+      for (int j = k >> 1; j > 0; j >>= 1) {
+        for (int i = lane; i < norm_cap; i += 32) {
+          const int l = i ^ j;
+          if (l > i) {
+            const double a = buf[i], b = buf[l];
+            const bool up = (i & k) == 0;
+            if ((a > b) == up) { buf[i] = b; buf[l] = a; }
+          }
+        }
+        __syncwarp();
+      }
+    }
+    if (count == 0) med = __longlong_as_double(0x7ff8000000000000LL);
+    else if (count & 1) med = buf[count >> 1];
+    else med = (buf[(count >> 1) - 1] + buf[count >> 1]) * 0.5;
+    __syncwarp();
+  }
+  const double invmed = 1.0 / med;
+  const double invmed2 = 1.0 / (med * med);
+
+  // ---- window pixels: bordered Gram matrix on the tensor path ----------------------------------------
+  const int grp = lane >> 2, tig = lane & 3;
+  double acc[6][2];  // blocks (0,0) (1,0) (1,1) (2,0) (2,1) (2,2)
+#pragma unroll
+  for (int b = 0; b < 6; ++b) acc[b][0] = acc[b][1] = 0.0;
+  LogProd vprod;
+  int n_sel = 0;
+  for (int c0 = lo; c0 < hi_end; c0 += 32) {
+    // per-pixel scalars, one pixel per lane
+    const int p = c0 + lane;
+    const int pc = min(p, n_raw - 1);
+    const double xp = __ddiv_rn(X[pc], opz);  // emitted_wavelengths (:139)
+    const bool sel = p < hi_end && !sp.mask[pc] && xp >= prm.min_lambda && xp <= prm.max_lambda;  // :169-170
+    const int iv = zqso_interval(model, fmin(fmax(xp, model.rest[0]), model.rest[model.n_rest - 1]));
+    const double xoff = xp - model.rest[iv];
+    const double vn = sp.V[pc] * invmed2;
+    const double mu_p = fma(model.mu_slope[iv], xoff, model.mu[iv]);
+    double r = fma(sp.Y[pc], invmed, -mu_p);
+    double dinv = zq_rcp(vn);
+    if (!sel) { r = 0.0; dinv = 0.0; }
+    vprod.mul(sel ? vn : 1.0);
+    n_sel += sel ? 1 : 0;
+    if (((c0 - lo) & 255) == 224) vprod.renorm();
+#pragma unroll
+    for (int kb = 0; kb < 8; ++kb) {
+      const int src = kb * 4 + tig;
+      const int iv_k = __shfl_sync(0xffffffffu, iv, src);
+      const double xo_k = __shfl_sync(0xffffffffu, xoff, src);
+      const double di_k = __shfl_sync(0xffffffffu, dinv, src);
+      const double r_k = __shfl_sync(0xffffffffu, r, src);
+      const double* Mrow = model.M + (size_t)iv_k * ZQ_STRIDE + grp;
+      const double* Srow = model.M_slope + (size_t)iv_k * ZQ_STRIDE + grp;
+      const double m0 = fma(__ldg(Srow), xo_k, __ldg(Mrow));
+      const double m1 = fma(__ldg(Srow + 8), xo_k, __ldg(Mrow + 8));
+      double m2 = fma(__ldg(Srow + 16), xo_k, __ldg(Mrow + 16));  // columns 16..19, zero pads beyond
+      if (grp == 4) m2 = r_k;                                     // column 20 carries the residual
+      const double a0 = m0 * di_k, a1 = m1 * di_k, a2 = m2 * di_k;
+      zq_dmma(acc[0][0], acc[0][1], a0, m0);
+      zq_dmma(acc[1][0], acc[1][1], a1, m0);
+      zq_dmma(acc[2][0], acc[2][1], a1, m1);
+      zq_dmma(acc[3][0], acc[3][1], a2, m0);
+      zq_dmma(acc[4][0], acc[4][1], a2, m1);
+      zq_dmma(acc[5][0], acc[5][1], a2, m2);
+    }
+  }
+  const double sum_log_v = warp_sum(vprod.value());
+  const int n_in = (int)(warp_sum((double)n_sel) + 0.5);
+
+  // ---- fragments -> T (24 x 24, lower blocks), Cholesky of the bordered 21 x 21 matrix -------------------
+  double* T = buf;
+  {
+    const int bi_of[6] = {0, 1, 1, 2, 2, 2}, bj_of[6] = {0, 0, 1, 0, 1, 2};
+#pragma unroll
+    for (int b = 0; b < 6; ++b) {
+      const int row = bi_of[b] * 8 + grp, col = bj_of[b] * 8 + tig * 2;
+      T[row * ZQ_TSTRIDE + col] = acc[b][0];
+      T[row * ZQ_TSTRIDE + col + 1] = acc[b][1];
+    }
+  }
+  __syncwarp();
+  if (lane < ZQ_K) T[lane * ZQ_TSTRIDE + lane] += 1.0;  // + I (null_gp.py:341)
+  __syncwarp();
+  double piv_prod = 1.0;
+  for (int j = 0; j < ZQ_K; ++j) {
+    const double piv = T[j * ZQ_TSTRIDE + j];
+    piv_prod *= piv;
+    const double inv = 1.0 / sqrt(piv);
+    __syncwarp();
+    if (lane > j && lane <= ZQ_K) T[lane * ZQ_TSTRIDE + j] *= inv;  // column j of L, rows j+1..20
+    __syncwarp();
+    // trailing update of the lower triangle: rows i in (j, 20], columns k in (j, i]
+    const int m = ZQ_K - j;                 // remaining rows
+    const int pairs = m * (m + 1) / 2;
+    for (int e = lane; e < pairs; e += 32) {
+      // e -> (ii, kk), 0 <= kk <= ii < m
+      int ii = (int)((sqrt(8.0 * e + 1.0) - 1.0) * 0.5);
+      while ((ii + 1) * (ii + 2) / 2 <= e) ++ii;
+      while (ii * (ii + 1) / 2 > e) --ii;
+      const int kk = e - ii * (ii + 1) / 2;
+      const int i = j + 1 + ii, k = j + 1 + kk;
+      T[i * ZQ_TSTRIDE + k] = fma(-T[i * ZQ_TSTRIDE + j], T[k * ZQ_TSTRIDE + j], T[i * ZQ_TSTRIDE + k]);
+    }
+    __syncwarp();
+  }
+  const double quad = T[ZQ_K * ZQ_TSTRIDE + ZQ_K];  // q - z'z
+  const double ll_window = -0.5 * (quad + (sum_log_v + log(piv_prod)) + (double)n_in * ZQ_LOG_2PI);
+
+  // ---- i.i.d. Gaussians bluewards and redwards of the window (:160-166, :198-210, :252-278) -----------------
+  double side_ll[2];
+#pragma unroll
+  for (int side = 0; side < 2; ++side) {
+    const int begin = side == 0 ? 0 : rw_begin, end = side == 0 ? bw_end : n_raw;
+    const double m_side = side == 0 ? model.bluewards_mu : model.redwards_mu;
+    const double var_side = side == 0 ? model.bluewards_var : model.redwards_var;
+    double qs = 0.0;
+    LogProd dprod;
+    int cnt = 0, it = 0;
+    for (int p = begin + lane; p < end; p += 32, ++it) {
+      if (!sp.mask[p]) {
+        const double t = fma(sp.Y[p], invmed, -m_side);
+        const double dd = fma(sp.V[p], invmed2, var_side);
+        qs = fma(t * t, zq_rcp(dd), qs);
+        dprod.mul(dd);
+        ++cnt;
+      }
+      if ((it & 7) == 7) dprod.renorm();
+    }
+    const double q_tot = warp_sum(qs), ld_tot = warp_sum(dprod.value());
+    const int c_tot = (int)(warp_sum((double)cnt) + 0.5);
+    side_ll[side] = -0.5 * (q_tot + ld_tot + (double)c_tot * ZQ_LOG_2PI);
+  }
+  if (lane == 0) *out_ll = ll_window + side_ll[0] + side_ll[1];
+}
+
+// np.nanargmax over the samples of each spectrum (first maximum wins); -1 when every sample is NaN
+__global__ void __launch_bounds__(256) zqso_argmax_kernel(const double* __restrict__ ll, int S, const double* z_samples,
+                                                          double* z_map, int32_t* map_index) {
+  __shared__ double s_val[256];
+  __shared__ int s_idx[256];
+  const double* row = ll + (size_t)blockIdx.x * S;
+  double best = 0.0;
+  int bi = -1;
+  for (int i = threadIdx.x; i < S; i += blockDim.x) {
+    const double v = row[i];
+    if (!isnan(v) && (bi < 0 || v > best)) { best = v; bi = i; }
+  }
+  s_val[threadIdx.x] = best;
+  s_idx[threadIdx.x] = bi;
+  __syncthreads();
+  for (int off = 128; off > 0; off >>= 1) {
+    if (threadIdx.x < off) {
+      const int oi = s_idx[threadIdx.x + off];
+      const double ov = s_val[threadIdx.x + off];
+      const int ci = s_idx[threadIdx.x];
+      const double cv = s_val[threadIdx.x];
+      if (oi >= 0 && (ci < 0 || ov > cv || (ov == cv && oi < ci))) { s_val[threadIdx.x] = ov; s_idx[threadIdx.x] = oi; }
+    }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    const int i = s_idx[0];
+    map_index[blockIdx.x] = i;
+    z_map[blockIdx.x] = i >= 0 ? z_samples[i] : __longlong_as_double(0x7ff8000000000000LL);
+  }
+}
+
+// ZGP.set_data + get_interp at ONE redshift, element-wise over the raw pixels (attribute path; exact
+// two-rounding interpolation arithmetic of scipy interp1d).  cls: 0 none, 1 modelled, 2 bluewards, 3 redwards.
+// The median is computed by the likelihood kernel's sorter (launched with one sample) and passed in.
+__global__ void zqso_set_data_kernel(ZqsoSpectrum sp, double z, ZqsoModelDev model, ZqsoParamsDev prm, double med,
+                                     double* x, double* yn, double* vn, double* this_mu, double* this_M /* n_raw x k */,
+                                     uint8_t* cls, uint8_t* in_window) {
+  const int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= sp.n_raw) return;
+  const double opz = __dadd_rn(1.0, z);
+  const double max_pos = __dmul_rn(prm.max_lambda, opz), min_pos = __dmul_rn(prm.min_lambda, opz);
+  const double max_obs = fmin(max_pos, sp.X[sp.n_raw - 1]), min_obs = fmax(min_pos, sp.X[0]);
+  const double X = sp.X[p];
+  const double xp = __ddiv_rn(X, opz);
+  const bool inw = X > min_obs && X < max_obs;
+  const bool masked = sp.mask[p] != 0;
+  x[p] = xp;
+  yn[p] = __ddiv_rn(sp.Y[p], med);
+  vn[p] = __ddiv_rn(sp.V[p], __dmul_rn(med, med));
+  uint8_t c = 0;
+  if (inw && !masked && xp >= prm.min_lambda && xp <= prm.max_lambda) c = 1;
+  else if (X < min_obs && !masked) c = 2;
+  else if (X > max_obs && !masked) c = 3;
+  cls[p] = c;
+  in_window[p] = inw ? 1 : 0;
+  if (c == 1) {
+    const int iv = zqso_interval(model, xp);
+    const double xoff = __dsub_rn(xp, model.rest[iv]);
+    this_mu[p] = __dadd_rn(__dmul_rn(model.mu_slope[iv], xoff), model.mu[iv]);
+    for (int j = 0; j < ZQ_K; ++j)
+      this_M[(size_t)p * ZQ_K + j] =
+          __dadd_rn(__dmul_rn(model.M_slope[(size_t)iv * ZQ_STRIDE + j], xoff), model.M[(size_t)iv * ZQ_STRIDE + j]);
+  }
+}
+
+// nanmedian of the normalisation window at one redshift (same sorter as the likelihood kernel), one warp
+__global__ void zqso_median_kernel(ZqsoSpectrum sp, double z, ZqsoParamsDev prm, int norm_cap, double* med_out) {
+  extern __shared__ double zq_smem[];
+  const int lane = threadIdx.x & 31;
+  double* buf = zq_smem;
+  const double opz = __dadd_rn(1.0, z);
+  const double max_pos = __dmul_rn(prm.max_lambda, opz), min_pos = __dmul_rn(prm.min_lambda, opz);
+  const double max_obs = fmin(max_pos, sp.X[sp.n_raw - 1]), min_obs = fmax(min_pos, sp.X[0]);
+  const int lo = zq_bound(sp.X, 0, sp.n_raw, min_obs, true);
+  const int hi_end = zq_bound(sp.X, 0, sp.n_raw, max_obs, false);
+  const int nlo = zq_bound_rest(sp.X, opz, lo, max(hi_end, lo), prm.norm_min_lambda, false);
+  const int nhi = zq_bound_rest(sp.X, opz, lo, max(hi_end, lo), prm.norm_max_lambda, true);
+  const double inf = __longlong_as_double(0x7ff0000000000000LL);
+  int count = 0;
+  for (int i = lane; i < norm_cap; i += 32) {
+    const int p = nlo + i;
+    double val = inf;
+    if (p < nhi) {
+      const double yv = sp.Y[p];
+      if (!isnan(yv)) { val = yv; ++count; }
+    }
+    buf[i] = val;
+  }
+  count = (int)(warp_sum((double)count) + 0.5);
+  __syncwarp();
+  for (int k = 2; k <= norm_cap; k <<= 1)
+    for (int j = k >> 1; j > 0; j >>= 1) {
+      for (int i = lane; i < norm_cap; i += 32) {
+        const int l = i ^ j;
+        if (l > i) {
+          const double a = buf[i], b = buf[l];
+          const bool up = (i & k) == 0;
+          if ((a > b) == up) { buf[i] = b; buf[l] = a; }
+        }
+      }
+      __syncwarp();
+    }
+  if (lane == 0) {
+    double med;
+    if (count == 0) med = __longlong_as_double(0x7ff8000000000000LL);
+    else if (count & 1) med = buf[count >> 1];
+    else med = (buf[(count >> 1) - 1] + buf[count >> 1]) * 0.5;
+    *med_out = med;
+  }
+}
+
+// log N(y; mu, diag(d)) (zqso_gp.py:252-278), one CTA
+__global__ void __launch_bounds__(256) log_mvnpdf_iid_kernel(const double* y, const double* mu, const double* d, int n,
+                                                             double* out) {
+  __shared__ double red[2][8];
+  double q = 0.0, ld = 0.0;
+  for (int p = threadIdx.x; p < n; p += blockDim.x) {
+    const double r = y[p] - mu[p];
+    q = fma(r / d[p], r, q);
+    ld += log(d[p]);
+  }
+  q = warp_sum(q);
+  ld = warp_sum(ld);
+  if ((threadIdx.x & 31) == 0) { red[0][threadIdx.x >> 5] = q; red[1][threadIdx.x >> 5] = ld; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    q = 0.0; ld = 0.0;
+    for (int w = 0; w < 8; ++w) { q += red[0][w]; ld += red[1][w]; }
+    out[0] = -0.5 * (q + ld + (double)n * ZQ_LOG_2PI);
+  }
+}
+
+}  // namespace dla

@@ -185,6 +185,38 @@ int dla_catalogue_run_staged(dla_catalogue* cat, dla_catalogue_outputs* outputs)
 int dla_catalogue_last_timing(const dla_catalogue* cat, double* total_ms, double* gram_ms,
                               double* voigt_ms, long long* launches, double* gram_flops);
 
+/* ---- a14: quasar-redshift estimation, ZGP (zqso_gp.py) ---------------------------------- */
+typedef struct dla_zqso_model dla_zqso_model; /* learned zQSO model resident on the device */
+/* ZGP.__init__ (zqso_gp.py:36-64): rest grid (n_rest), mu (n_rest), M (n_rest, k = 20) row-major, and the
+ * means / standard deviations of the i.i.d. models outside the modelling window */
+int dla_zqso_model_create(const double* rest_wavelengths, const double* mu, const double* M, int n_rest, int k,
+                          double bluewards_mu, double redwards_mu, double bluewards_sigma,
+                          double redwards_sigma, dla_zqso_model** out);
+int dla_zqso_model_destroy(dla_zqso_model* model);
+/* the attributes of ZParameters the path reads (zqso_set_parameters.py:19-54) */
+typedef struct dla_zqso_params {
+  double min_lambda, max_lambda;                             /* modelling window, rest A */
+  double normalization_min_lambda, normalization_max_lambda; /* flux normalisation window, rest A */
+} dla_zqso_params;
+/* ZGP.inference_z_qso (zqso_gp.py:214-250) for num_spectra ragged spectra (observed wavelengths,
+ * strictly increasing per spectrum) and S candidate redshifts shared by all spectra.
+ * sample_log_likelihoods (num_spectra, S) may be NULL; z_map (num_spectra) = z of np.nanargmax, NaN and
+ * map_index -1 when every sample is NaN (the reference raises ValueError there). */
+int dla_zqso_inference(const dla_zqso_model* model, const dla_zqso_params* params, int num_spectra,
+                       const int64_t* pixel_offsets, const double* wavelengths, const double* flux,
+                       const double* noise_variance, const uint8_t* pixel_mask, const double* z_samples,
+                       int S, double* sample_log_likelihoods, double* z_map, int32_t* map_index);
+/* ZGP.set_data + get_interp at one redshift (zqso_gp.py:66-182), element-wise over the n_raw pixels:
+ * x = X / (1 + z), normalised flux / variance, interpolated mu (n_raw) and M (n_raw, k) where cls == 1,
+ * cls (0 none, 1 modelled, 2 bluewards, 3 redwards), in_window (the first `ind` of :132), this_median.
+ * The caller selects rows by cls (boolean indexing) to form the reference's attributes. */
+int dla_zqso_set_data(const dla_zqso_model* model, const dla_zqso_params* params, const double* X,
+                      const double* Y, const double* noise_variance, const uint8_t* pixel_mask, int n_raw,
+                      double z_qso, double* x, double* y_normalized, double* v_normalized, double* this_mu,
+                      double* this_M, uint8_t* cls, uint8_t* in_window, double* this_median);
+/* ZGP.log_mvnpdf_iid (zqso_gp.py:252-278) */
+int dla_log_mvnpdf_iid(const double* y, const double* mu, const double* d, int n, double* out);
+
 #ifdef __cplusplus
 }
 #endif
