@@ -9,27 +9,28 @@
 //     w_sp = a_sp^2 / d_sp ,  g_sp = a_sp r_sp / d_sp ,  r_sp = y_p - mu_p a_sp
 // the per-sample Gram matrices and projections are ONE dense FP64 contraction over pixels
 //     [B_s - I | c_s] = [W | G] x [P | M] ,   P[p,(i,j)] = m_pi m_pj  (i >= j, 210 pairs)
-// on the FP64 tensor path (DMMA m8n8k4; on B200 it shares the 64 FMA lanes/SM/clk of the DFMA
-// pipe - 37 TFLOP/s measured either way - so every scalar FP64 instruction in this kernel is
-// paid for with DMMA slots).  Structure, per CTA of 32 samples x 8 warps (two CTAs per SM):
+// on the FP64 tensor path (DMMA m8n8k4).
+//
+// The design follows from one measured fact: on B200 the DMMA path and the scalar FP64 pipe are
+// the same 64 FMA lanes/SM/clk (37 TFLOP/s either way; mixed stream 35).  A scalar FP64 instruction
+// issued while DMMAs saturate that pipe waits for a DMMA slot (16 cycles each, several queued), so
+// a dependent chain of a dozen scalar operations costs a warp more time than its 60 DMMAs - measured:
+// the overlapped version of this kernel ran at 22 TFLOP/s, 30 with the producer arithmetic removed.
+// So scalar and tensor work are SEPARATED IN TIME instead of overlapped:
+//   * one CTA of 16 warps per SM owns 64 samples and walks the pixels in 32-pixel panels;
+//   * phase A (all warps, no DMMA in flight): every thread turns 4 profile-cache elements (product of
+//     up to 8 absorber factors, dla_gp.py:370-386, loaded during the previous phase B) into the W / G
+//     operand tiles - MUFU-seeded Newton reciprocal, integer-renormalised running product for
+//     sum log d (one log per lane per tile); uncontended, the whole phase is a few hundred cycles;
+//   * phase B (all warps, nothing but LDS + DMMA): warp (rq, cq) owns 16 samples x 7 or 8 of the 30
+//     column blocks, sized [8,7,8,7] / [7,8,7,8] by row quarter so that the four warps of every SM
+//     sub-partition issue 120 DMMAs per 4 pixels: no padding block, four balanced pipes; the loads
+//     of the next panel's profile rows are in flight underneath;
 //   * the Gram basis [P | M] of the spectrum (n x 240, precomputed once by gram_basis_kernel,
-//     L2-resident) streams through shared memory in 16-pixel panels by TMA bulk copies
-//     (cp.async.bulk + mbarrier complete_tx): no DMUL and no column-index registers in the MMA loop;
-//   * every warp is producer AND consumer (warps that only produce starve behind warps that only
-//     issue DMMAs - measured): it turns its 2 x 16 share of the profile-cache rows (product of up to
-//     8 absorber factors, dla_gp.py:370-386, prefetched one panel ahead in registers) into the W / G
-//     operand tiles of the NEXT panel - MUFU-seeded Newton reciprocal, integer-renormalised running
-//     product for sum log d (one log per lane per tile) - then runs its DMMAs on the current one;
-//   * warp (rh, cq) owns 16 samples x 7 or 8 of the 30 column blocks, sized [8,7,8,7] / [7,8,7,8]
-//     so that the two warps of every SM sub-partition issue 30 DMMAs per 4 pixels: no padding
-//     block, four balanced FP64 pipes;
-//   * no CTA-wide barrier in the main loop: W/G tiles go through a 4-deep ring (mbarrier with 8 warp
-//     arrivals per stage), basis panels through a 2-deep ring whose refill is requested by the LAST
-//     warp to leave the stage (shared-memory counter), so nobody ever waits for a stage to drain and
-//     warps drift by up to a panel;
-//   * the bordered 21 x 21 Cholesky (factor, z = L^-1 c, log-det) of every sample runs in shared
-//     memory straight out of the accumulator fragments while the SM's other CTA keeps the
-//     tensor pipe busy.
+//     L2-resident) streams through a 2-deep shared-memory ring by TMA bulk copies
+//     (cp.async.bulk + mbarrier complete_tx), requested a full panel ahead;
+//   * the bordered 21 x 21 Cholesky (factor, z = L^-1 c, log-det) of the 64 samples is a third,
+//     purely scalar phase: 8 threads per sample, straight out of the accumulator fragments.
 // HBM sees only the profile rows (read) and one double per sample (written).
 #pragma once
 #include <stdint.h>
@@ -39,23 +40,23 @@ namespace dla {
 
 constexpr int LK_K = 20;                         // rank of the learned covariance (Parameters.k)
 constexpr int LK_PAIRS = LK_K * (LK_K + 1) / 2;  // 210 lower-triangle pairs
-constexpr int LK_TS = 32;                        // samples per CTA tile
-constexpr int LK_KC = 16;                        // pixels per panel
-constexpr int LK_WSTRIDE = LK_KC + 4;            // row stride of the W/G tiles (20 == 4 mod 16: conflict-free A loads)
+constexpr int LK_TS = 64;                        // samples per CTA tile
+constexpr int LK_KC = 32;                        // pixels per panel
+constexpr int LK_WSTRIDE = LK_KC + 4;            // row stride of the W/G tiles (36 == 4 mod 16: conflict-free A loads)
 constexpr int LK_NBLK_PAIR = 27;                 // ceil(210 / 8) column blocks of the Gram part
 constexpr int LK_NBLK = 30;                      // + 3 column blocks (24 >= 20) of the projection part
 constexpr int LK_NCOLS = LK_NBLK * 8;            // 240
 constexpr int LK_PSTRIDE = LK_NCOLS + 4;         // basis row stride (244 == 4 mod 16: conflict-free B loads)
 constexpr int LK_PROJ_COL0 = LK_NBLK_PAIR * 8;   // 216: first projection column
-constexpr int LK_WARPS = 8;
-constexpr int LK_THREADS = LK_WARPS * 32;        // 256
+constexpr int LK_WARPS = 16;
+constexpr int LK_THREADS = LK_WARPS * 32;        // 512
 constexpr int LK_PSTAGES = 2;                    // basis-panel ring (TMA)
-constexpr int LK_WSTAGES = 4;                    // W/G operand ring
-constexpr int LK_EP_STRIDE = LK_TS + 1;          // epilogue smem: [col][sample], stride 33
+constexpr int LK_EP_STRIDE = LK_TS + 1;          // epilogue smem: [col][sample], stride 65
+constexpr int LK_EP_THREADS = 8;                 // threads per sample in the Cholesky phase
 constexpr int LK_MAX_ROWS = 8;                   // max absorbers multiplied per sample (max_dlas <= 8)
 constexpr int LK_MB = 2;                         // DMMA row blocks per warp (16 samples)
 constexpr int LK_NB_MAX = 8;                     // DMMA column blocks per warp (7 or 8)
-constexpr int LK_EPT = LK_TS * LK_KC / LK_THREADS;  // W/G elements per thread per panel (2)
+constexpr int LK_EPT = LK_TS * LK_KC / LK_THREADS;  // W/G elements per thread per panel (4)
 constexpr double LK_LOG_2PI = 1.83787706640934534;  // null_gp.py:325
 constexpr double LK_LN2 = 0.693147180559945309417232121458;
 
@@ -151,36 +152,53 @@ __device__ __forceinline__ void tma_bulk_g2s(uint32_t dst, const void* src, uint
                ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
 }
 
-// 1/d for the operand tiles: MUFU.RCP64H seed (SFU, not the FP64 pipe) + two Newton steps (4 DFMA);
-// <= 1 ulp from the IEEE quotient on the normal range, IEEE division outside it.
+// cp.async (LDGSTS): global -> shared without a register round trip
+__device__ __forceinline__ void cp_async8(void* smem_dst, const void* gmem_src) {
+  const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"(d), "l"(gmem_src) : "memory");
+}
+__device__ __forceinline__ void cp_async16_zfill(void* smem_dst, const void* gmem_src, int src_bytes) {
+  const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(d), "l"(gmem_src), "r"(src_bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;\n" ::: "memory"); }
+
+// 1/d for the operand tiles: MUFU.RCP64H seed (SFU, not the FP64 pipe) + two Newton steps (4 DFMA),
+// <= 1 ulp from the IEEE quotient.  Branch-free, so the four elements of a thread interleave: outside
+// [1e-290, 1e290] (0, inf, NaN, negative: never produced by a valid spectrum) the seed itself is
+// returned, which has the IEEE special-value behaviour (1/inf = 0, 1/0 = inf, NaN stays NaN).
 __device__ __forceinline__ double fast_rcp(double d) {
-  if (!(d > 1e-290 && d < 1e290)) return 1.0 / d;
-  double r;
-  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(d));
-  double e = fma(-d, r, 1.0);
-  r = fma(r, e, r);
+  double r0;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r0) : "d"(d));
+  double e = fma(-d, r0, 1.0);
+  double r = fma(r0, e, r0);
   e = fma(-d, r, 1.0);
-  return fma(r, e, r);
+  r = fma(r, e, r);
+  return (d > 1e-290 && d < 1e290) ? r : r0;
 }
 
-// ---- shared memory plan (per CTA; two CTAs are resident per SM) -----------------------------------
-//   basis ring : 2 x [16][244]                                              62 464 B
-//   W/G ring   : 4 x { W [32][20] | G [32][20] }                            40 960 B
-//   E          : epilogue matrix [240][33], overlays the rings              63 360 B
-//   AUX        : per-sample sums [32][2], profile rows [8][32], mbarriers, drain counters
-constexpr int LK_PANEL_DOUBLES = LK_KC * LK_PSTRIDE;               // 3904
-constexpr int LK_WG_DOUBLES = LK_TS * LK_WSTRIDE;                  // 640
-constexpr uint32_t LK_PANEL_BYTES = LK_PANEL_DOUBLES * sizeof(double);  // 31 232
-constexpr int LK_RING_DOUBLES = LK_PSTAGES * LK_PANEL_DOUBLES + LK_WSTAGES * 2 * LK_WG_DOUBLES;  // 12 928
-constexpr int LK_EP_DOUBLES = LK_NCOLS * LK_EP_STRIDE;             // 7920
+// ---- shared memory plan (one CTA per SM) ------------------------------------------------------------
+//   basis ring : 2 x [32][244]                                             124 928 B
+//   W | G      : [64][36] each                                              36 864 B
+//   RAW        : profile-row panels of factor 0 and factor 1 [64][32] each, pixel scalars [4][32]
+//                (filled by cp.async during phase B, read in phase A)          33 792 B
+//   E          : epilogue matrix [240][65], overlays the above             124 800 B
+//   AUX        : per-sample sums [64][2], profile rows [8][64], 2 mbarriers
+constexpr int LK_PANEL_DOUBLES = LK_KC * LK_PSTRIDE;               // 7808
+constexpr int LK_WG_DOUBLES = LK_TS * LK_WSTRIDE;                  // 2304
+constexpr uint32_t LK_PANEL_BYTES = LK_PANEL_DOUBLES * sizeof(double);  // 62 464
+constexpr int LK_RAW_DOUBLES = 2 * LK_TS * LK_KC + 4 * LK_KC;       // 4224
+constexpr int LK_RING_DOUBLES = LK_PSTAGES * LK_PANEL_DOUBLES + 2 * LK_WG_DOUBLES + LK_RAW_DOUBLES;  // 24 448
+constexpr int LK_EP_DOUBLES = LK_NCOLS * LK_EP_STRIDE;             // 15 600
 constexpr int LK_MAIN_DOUBLES = LK_RING_DOUBLES > LK_EP_DOUBLES ? LK_RING_DOUBLES : LK_EP_DOUBLES;
 constexpr size_t LK_AUX_BYTES = LK_TS * 2 * sizeof(double) + LK_MAX_ROWS * LK_TS * sizeof(int32_t) +
-                                (LK_PSTAGES + LK_WSTAGES) * sizeof(uint64_t) + LK_PSTAGES * sizeof(int);
+                                LK_PSTAGES * sizeof(uint64_t);
 constexpr size_t LK_SMEM_BYTES = (size_t)LK_MAIN_DOUBLES * sizeof(double) + LK_AUX_BYTES;
 static_assert(LK_PANEL_BYTES % 128 == 0, "TMA alignment");
 
-// grid = (ceil(max num_samples / 32), num_spectra), block = 256, dynamic smem = LK_SMEM_BYTES
-__global__ void __launch_bounds__(LK_THREADS, 2)
+// grid = (ceil(max num_samples / 64), num_spectra), block = 512, dynamic smem = LK_SMEM_BYTES
+__global__ void __launch_bounds__(LK_THREADS, 1)
 sample_likelihood_kernel(const LikelihoodSpectrum* __restrict__ specs) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   const LikelihoodSpectrum sp = specs[blockIdx.y];
@@ -189,10 +207,14 @@ sample_likelihood_kernel(const LikelihoodSpectrum* __restrict__ specs) {
   if (sp.alive && *sp.alive == 0) return;
 
   double* s_main = reinterpret_cast<double*>(smem_raw);
-  double* s_sums = s_main + LK_MAIN_DOUBLES;                          // [32][2] : sum r^2/d, sum log d
-  int32_t* s_rows = reinterpret_cast<int32_t*>(s_sums + LK_TS * 2);   // [num_rows][32]
-  uint64_t* s_mbar = reinterpret_cast<uint64_t*>(s_rows + LK_MAX_ROWS * LK_TS);  // panel[2], wg[4]
-  int* s_drain = reinterpret_cast<int*>(s_mbar + LK_PSTAGES + LK_WSTAGES);       // [2] warps done with a basis stage
+  double* s_W = s_main + LK_PSTAGES * LK_PANEL_DOUBLES;
+  double* s_G = s_W + LK_WG_DOUBLES;
+  double* s_raw0 = s_G + LK_WG_DOUBLES;      // [64][32] factor-0 profile values of the staged panel
+  double* s_raw1 = s_raw0 + LK_TS * LK_KC;   // [64][32] factor-1 profile values
+  double* s_pix = s_raw1 + LK_TS * LK_KC;    // [4][32]  y, mu, omega2, v of the staged panel
+  double* s_sums = s_main + LK_MAIN_DOUBLES;                          // [64][2] : sum r^2/d, sum log d
+  int32_t* s_rows = reinterpret_cast<int32_t*>(s_sums + LK_TS * 2);   // [num_rows][64]
+  uint64_t* s_mbar = reinterpret_cast<uint64_t*>(s_rows + LK_MAX_ROWS * LK_TS);  // basis panel landed [2]
 
   const int tid = threadIdx.x;
   const int warp = tid >> 5, lane = tid & 31;
@@ -200,9 +222,14 @@ sample_likelihood_kernel(const LikelihoodSpectrum* __restrict__ specs) {
   const int npanels = (n + LK_KC - 1) / LK_KC;
   const int num_rows = sp.num_rows;
   const uint32_t bar_base = (uint32_t)__cvta_generic_to_shared(s_mbar);
-  auto panel_bar = [&](int stage) { return bar_base + 8u * stage; };             // basis panel landed (TMA bytes)
-  auto wg_bar = [&](int stage) { return bar_base + 8u * (LK_PSTAGES + stage); };   // W/G written by the 8 warps
-  double* s_wg = s_main + LK_PSTAGES * LK_PANEL_DOUBLES;
+
+  // basis panel `panel` -> its ring stage (one thread; completion is the stage's mbarrier)
+  auto issue_panel = [&](int panel) {
+    const int stage = panel & (LK_PSTAGES - 1);
+    mbar_expect_tx(bar_base + 8u * stage, LK_PANEL_BYTES);
+    tma_bulk_g2s((uint32_t)__cvta_generic_to_shared(s_main + stage * LK_PANEL_DOUBLES),
+                 sp.P + (size_t)panel * LK_PANEL_DOUBLES, LK_PANEL_BYTES, bar_base + 8u * stage);
+  };
 
   // ---- profile rows of the tile's samples, barriers -------------------------------------------
   for (int e = tid; e < num_rows * LK_TS; e += LK_THREADS) {
@@ -215,39 +242,21 @@ sample_likelihood_kernel(const LikelihoodSpectrum* __restrict__ specs) {
     }
     s_rows[r * LK_TS + s] = row;
   }
-  // basis panel `panel` -> its ring stage (one thread; completion is the stage's mbarrier)
-  auto issue_panel = [&](int panel) {
-    const int stage = panel & (LK_PSTAGES - 1);
-    mbar_expect_tx(panel_bar(stage), LK_PANEL_BYTES);
-    tma_bulk_g2s((uint32_t)__cvta_generic_to_shared(s_main + stage * LK_PANEL_DOUBLES),
-                 sp.P + (size_t)panel * LK_PANEL_DOUBLES, LK_PANEL_BYTES, panel_bar(stage));
-  };
   if (tid == 0) {
 #pragma unroll
-    for (int s = 0; s < LK_PSTAGES; ++s) { mbar_init(panel_bar(s), 1); s_drain[s] = 0; }
-#pragma unroll
-    for (int s = 0; s < LK_WSTAGES; ++s) mbar_init(wg_bar(s), LK_WARPS);
+    for (int s = 0; s < LK_PSTAGES; ++s) mbar_init(bar_base + 8u * s, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    for (int c = 0; c < LK_PSTAGES && c < npanels; ++c) issue_panel(c);
+    issue_panel(0);
   }
   __syncthreads();
 
-  // ---- producer role: thread -> pixel lane pl of the panel, samples sgrp and sgrp + 16 ------------
-  // (a half-warp stores 16 consecutive doubles of one W/G row: conflict-free; and reads 128
-  //  contiguous bytes of a profile row)
-  const int pl = tid & (LK_KC - 1);
-  const int sgrp = tid >> 4;  // 0..15
+  // ---- producer role: warp w -> samples w, w+16, w+32, w+48 ; lane -> pixel of the panel -----------
+  // (a warp stores 32 consecutive doubles of one W/G row: conflict-free; and reads 256 contiguous
+  //  bytes of a profile row)
   const bool two_rows = num_rows > 1;
-  bool live[LK_EPT];
-  const double* rowp0[LK_EPT];
-  const double* rowp1[LK_EPT];
+  unsigned live = 0;
 #pragma unroll
-  for (int e = 0; e < LK_EPT; ++e) {
-    const int s = sgrp + 16 * e;
-    live[e] = tile_s0 + s < sp.num_samples;
-    rowp0[e] = sp.base0 + (size_t)s_rows[s] * sp.ld;
-    rowp1[e] = two_rows ? sp.cache + (size_t)s_rows[LK_TS + s] * sp.ld : rowp0[e];
-  }
+  for (int e = 0; e < LK_EPT; ++e) live |= (tile_s0 + warp + LK_WARPS * e < sp.num_samples ? 1u : 0u) << e;
   double q_acc[LK_EPT], dprod[LK_EPT];
   int esum[LK_EPT];
 #pragma unroll
@@ -267,74 +276,77 @@ sample_likelihood_kernel(const LikelihoodSpectrum* __restrict__ specs) {
     }
   };
 
-  // register buffer of the next panel's inputs (loads issued one panel ahead).  The loads are
-  // unconditional on clamped addresses - a predicated load drags a dependent select behind it and
-  // the warp would sit on the DRAM latency instead of running its DMMAs; validity is applied at use.
-  double f0[LK_EPT], f1[LK_EPT], yp, mup, omp, vp;
-  auto load_panel = [&](int panel) {
-    const int p = min(panel * LK_KC + pl, n - 1);
-#pragma unroll
-    for (int e = 0; e < LK_EPT; ++e) {
-      f0[e] = __ldg(rowp0[e] + p);
-      f1[e] = __ldg(rowp1[e] + p);
+  // stage the inputs of `panel` in shared memory with cp.async: issued at the start of phase B, so the
+  // copies fly underneath the DMMAs and no register is held for them (a register prefetch of 4 elements
+  // x 2 factors spilled, and the spill store waited for the load)
+  auto stage_panel = [&](int panel) {
+    const int p0 = panel * LK_KC;
+    for (int idx = tid; idx < LK_TS * LK_KC / 2; idx += LK_THREADS) {  // 16-byte chunks: 16 per sample row
+      const int s = idx >> 4, j = (idx & 15) * 2;
+      const int p = p0 + j;
+      const int ok = p < sp.ld ? 16 : 0;  // rows are padded to ld (multiple of 4): zero-fill beyond
+      const size_t off = (size_t)min(p, sp.ld - 2);
+      cp_async16_zfill(s_raw0 + s * LK_KC + j, sp.base0 + (size_t)s_rows[s] * sp.ld + off, ok);
+      if (two_rows) cp_async16_zfill(s_raw1 + s * LK_KC + j, sp.cache + (size_t)s_rows[LK_TS + s] * sp.ld + off, ok);
     }
-    yp = __ldg(sp.y + p);
-    mup = __ldg(sp.mu + p);
-    omp = __ldg(sp.omega2 + p);
-    vp = __ldg(sp.v + p);
+    if (tid < 4 * LK_KC) {
+      const int arr = tid >> 5, j = tid & 31;
+      const double* src = arr == 0 ? sp.y : arr == 1 ? sp.mu : arr == 2 ? sp.omega2 : sp.v;
+      cp_async8(s_pix + arr * LK_KC + j, src + min(p0 + j, n - 1));
+    }
+    cp_async_commit();
   };
 
-  // W/G tiles of `panel` into stage panel % 4.  No wait: a warp can only be here after the basis
-  // panel of `panel - 1` landed, which was requested after ALL warps finished panel - 3 (the previous
-  // user of this W/G stage).
+  // phase A: W/G tiles of `panel`.  Branch-free over the four elements of a thread so that their
+  // dependent chains (load, products, reciprocal, ...) interleave; validity is a select at the end.
   auto produce = [&](int panel) {
-    double* Ws = s_wg + (panel & (LK_WSTAGES - 1)) * (2 * LK_WG_DOUBLES);
-    double* Gs = Ws + LK_WG_DOUBLES;
-    const int p = panel * LK_KC + pl;
+    const int p = panel * LK_KC + lane;
     const bool pv = p < n;
-    double w[LK_EPT], g[LK_EPT];
+    const double yp = s_pix[lane], mup = s_pix[LK_KC + lane], omp = s_pix[2 * LK_KC + lane], vp = s_pix[3 * LK_KC + lane];
+    double a[LK_EPT];
+#pragma unroll
+    for (int e = 0; e < LK_EPT; ++e) a[e] = s_raw0[(warp + LK_WARPS * e) * LK_KC + lane];
+    // absorption = product of the factors' profiles, left to right (dla_gp.py:370-386)
+    if (two_rows) {
+#pragma unroll
+      for (int e = 0; e < LK_EPT; ++e) a[e] = a[e] * s_raw1[(warp + LK_WARPS * e) * LK_KC + lane];
+    }
+    if (num_rows > 2) {  // rare: dla_sample_log_likelihoods with more than two absorbers per sample
+      const int pc = min(p, n - 1);
+#pragma unroll
+      for (int e = 0; e < LK_EPT; ++e)
+        for (int r = 2; r < num_rows; ++r)
+          a[e] = a[e] * sp.cache[(size_t)s_rows[r * LK_TS + warp + LK_WARPS * e] * sp.ld + pc];
+    }
 #pragma unroll
     for (int e = 0; e < LK_EPT; ++e) {
-      const int s = sgrp + 16 * e;
-      w[e] = 0.0;
-      g[e] = 0.0;
-      if (pv && live[e]) {
-        // absorption = product of the factors' profiles, left to right (dla_gp.py:370-386)
-        double a = f0[e];
-        if (two_rows) a = a * f1[e];
-        for (int r = 2; r < num_rows; ++r) a = a * sp.cache[(size_t)s_rows[r * LK_TS + s] * sp.ld + p];
-        if (sp.prod_out) sp.prod_out[(size_t)(tile_s0 + s) * sp.ld + p] = a;
-        const double a2 = a * a;
-        const double d = fma(omp, a2, vp);   // dla_omega2 + v
-        const double inv = fast_rcp(d);
-        const double r = fma(-mup, a, yp);   // y - dla_mu
-        const double t = r * inv;
-        w[e] = a2 * inv;
-        g[e] = a * t;
-        q_acc[e] = fma(r, t, q_acc[e]);
-        dprod[e] *= d;
-      }
+      const int s = warp + LK_WARPS * e;
+      const bool ok = pv && ((live >> e) & 1u);
+      if (ok && sp.prod_out) sp.prod_out[(size_t)(tile_s0 + s) * sp.ld + p] = a[e];
+      const double a2 = a[e] * a[e];
+      const double d = fma(omp, a2, vp);      // dla_omega2 + v
+      const double inv = fast_rcp(d);
+      const double r = fma(-mup, a[e], yp);   // y - dla_mu
+      const double t = r * inv;
+      s_W[s * LK_WSTRIDE + lane] = ok ? a2 * inv : 0.0;
+      s_G[s * LK_WSTRIDE + lane] = ok ? a[e] * t : 0.0;
+      q_acc[e] = ok ? fma(r, t, q_acc[e]) : q_acc[e];
+      dprod[e] = ok ? dprod[e] * d : dprod[e];
     }
-    if (panel + 1 < npanels) load_panel(panel + 1);  // in flight while this warp runs its DMMAs
-#pragma unroll
-    for (int e = 0; e < LK_EPT; ++e) {
-      Ws[(sgrp + 16 * e) * LK_WSTRIDE + pl] = w[e];
-      Gs[(sgrp + 16 * e) * LK_WSTRIDE + pl] = g[e];
-    }
-    __syncwarp();
-    if (lane == 0) mbar_arrive(wg_bar(panel & (LK_WSTAGES - 1)));
   };
 
-  // ---- MMA role: warp (rh, cq) owns samples 16 rh .. 16 rh + 15 and 7 or 8 column blocks -----------
-  //   rh = 0 : blocks [0,8) [8,15) [15,23) [23,30)      rh = 1 : blocks [0,7) [7,15) [15,22) [22,30)
+  // ---- MMA role: warp (rq, cq) owns samples 16 rq .. 16 rq + 15 and 7 or 8 column blocks -----------
+  //   rq even : blocks [0,8) [8,15) [15,23) [23,30)      rq odd : blocks [0,7) [7,15) [15,22) [22,30)
   // Blocks >= 27 are the projection part (A = G).  Local blocks 0..3 always take A = W, local block 4
   // and local blocks 5..7 read A through pointers (W or G), so all warps run one instruction stream
-  // with no predicated DMMA; the eighth block sits behind a warp-uniform branch.
+  // with no predicated DMMA (a predicated-off DMMA still occupies its pipe slot); the eighth block
+  // sits behind a warp-uniform branch.
   const int grp = lane >> 2;      // DMMA groupID
   const int tig = lane & 3;       // DMMA threadID_in_group
-  const int rh = warp >> 2, cq = warp & 3;
-  const int first = rh == 0 ? (cq == 0 ? 0 : cq == 1 ? 8 : cq == 2 ? 15 : 23) : (cq == 0 ? 0 : cq == 1 ? 7 : cq == 2 ? 15 : 22);
-  const bool has_eighth = ((cq + rh) & 1) == 0;
+  const int rq = warp >> 2, cq = warp & 3;
+  const bool odd = (rq & 1) != 0;
+  const int first = !odd ? (cq == 0 ? 0 : cq == 1 ? 8 : cq == 2 ? 15 : 23) : (cq == 0 ? 0 : cq == 1 ? 7 : cq == 2 ? 15 : 22);
+  const bool has_eighth = ((cq + (odd ? 1 : 0)) & 1) == 0;
   const bool g4 = first + 4 >= LK_NBLK_PAIR, g5 = first + 5 >= LK_NBLK_PAIR;
   double acc[LK_MB][LK_NB_MAX][2];
 #pragma unroll
@@ -342,17 +354,15 @@ sample_likelihood_kernel(const LikelihoodSpectrum* __restrict__ specs) {
 #pragma unroll
     for (int nb = 0; nb < LK_NB_MAX; ++nb) acc[m][nb][0] = acc[m][nb][1] = 0.0;
 
+  // phase B: DMMAs of `panel`
   auto consume = [&](int panel) {
-    const int pstage = panel & (LK_PSTAGES - 1), wstage = panel & (LK_WSTAGES - 1);
+    const int pstage = panel & (LK_PSTAGES - 1);
     const double* Ps = s_main + pstage * LK_PANEL_DOUBLES;
-    const double* Ws = s_wg + wstage * (2 * LK_WG_DOUBLES);
-    const double* Gs = Ws + LK_WG_DOUBLES;
-    mbar_wait(wg_bar(wstage), (panel / LK_WSTAGES) & 1);     // W/G written by all warps
-    mbar_wait(panel_bar(pstage), (panel / LK_PSTAGES) & 1);  // basis panel landed
-    const int aoff = (rh * 16 + grp) * LK_WSTRIDE + tig;
-    const double* arow = Ws + aoff;
-    const double* a4row = (g4 ? Gs : Ws) + aoff;
-    const double* a5row = (g5 ? Gs : Ws) + aoff;
+    mbar_wait(bar_base + 8u * pstage, (panel / LK_PSTAGES) & 1);  // basis panel landed
+    const int aoff = (rq * 16 + grp) * LK_WSTRIDE + tig;
+    const double* arow = s_W + aoff;
+    const double* a4row = (g4 ? s_G : s_W) + aoff;
+    const double* a5row = (g5 ? s_G : s_W) + aoff;
     const double* brow = Ps + tig * LK_PSTRIDE + first * 8 + grp;
 #pragma unroll
     for (int kb = 0; kb < LK_KC / 4; ++kb) {
@@ -390,50 +400,47 @@ sample_likelihood_kernel(const LikelihoodSpectrum* __restrict__ specs) {
           dmma884(acc[m][7][0], acc[m][7][1], a5row[m * 8 * LK_WSTRIDE + kb * 4], b);
       }
     }
-    if (panel + LK_PSTAGES < npanels) {
-      // the last warp to leave the basis stage requests the panel that reuses it: nobody waits
-      __syncwarp();
-      if (lane == 0 && atomicAdd(&s_drain[pstage], 1) == LK_WARPS - 1) {
-        s_drain[pstage] = 0;
-        issue_panel(panel + LK_PSTAGES);
-      }
-    }
   };
 
-  // ---- main loop: every warp produces panel c+1, then runs its DMMAs on panel c --------------------
-  load_panel(0);
-  produce(0);
+  // ---- main loop: phase A | barrier | phase B | barrier --------------------------------------------------
+  stage_panel(0);
+  cp_async_wait_all();
+  __syncthreads();
   for (int panel = 0; panel < npanels; ++panel) {
-    if (panel + 1 < npanels) produce(panel + 1);
+    if (tid == 0 && panel + 1 < npanels) issue_panel(panel + 1);  // its stage was drained by phase B of panel - 1
+    produce(panel);
+    __syncthreads();                                              // W/G complete, staged inputs consumed
+    if (panel + 1 < npanels) stage_panel(panel + 1);              // in flight underneath the DMMAs
     consume(panel);
-    if ((panel & 7) == 7) renorm();
+    if ((panel & 3) == 3) renorm();
+    cp_async_wait_all();
+    __syncthreads();                                              // W/G and the basis stage are free, inputs staged
   }
 
-  // per-sample scalar sums: reduce over the 16 pixel lanes of the half-warp
+  // per-sample scalar sums: reduce over the 32 pixel lanes
   renorm();
 #pragma unroll
   for (int e = 0; e < LK_EPT; ++e) {
     double q = q_acc[e];
     double l = fma((double)esum[e], LK_LN2, log(dprod[e]));
 #pragma unroll
-    for (int off = 8; off > 0; off >>= 1) {
+    for (int off = 16; off > 0; off >>= 1) {
       q += __shfl_xor_sync(0xffffffffu, q, off);
       l += __shfl_xor_sync(0xffffffffu, l, off);
     }
-    if (pl == 0) {
-      s_sums[(sgrp + 16 * e) * 2] = q;
-      s_sums[(sgrp + 16 * e) * 2 + 1] = l;
+    if (lane == 0) {
+      s_sums[(warp + LK_WARPS * e) * 2] = q;
+      s_sums[(warp + LK_WARPS * e) * 2 + 1] = l;
     }
   }
-  __syncthreads();  // every panel consumed by every warp; the stages can be overlaid
 
-  // ---- accumulators -> E[col][sample] -----------------------------------------------------------
+  // ---- accumulators -> E[col][sample] (overlays the ring; the last barrier of the loop freed it) --------
   double* E = s_main;
   {
     const int count = has_eighth ? 8 : 7;
 #pragma unroll
     for (int m = 0; m < LK_MB; ++m) {
-      const int s = rh * 16 + m * 8 + grp;
+      const int s = rq * 16 + m * 8 + grp;
 #pragma unroll
       for (int nb = 0; nb < LK_NB_MAX; ++nb) {
         if (nb < count) {
@@ -446,12 +453,12 @@ sample_likelihood_kernel(const LikelihoodSpectrum* __restrict__ specs) {
   }
   __syncthreads();
 
-  // ---- Cholesky of the bordered matrix [[B, c], [c', q]] : 4 threads per sample ------------
+  // ---- Cholesky of the bordered matrix [[B, c], [c', q]] : 8 threads per sample ------------
   // E col layout: pair (i,j) at i(i+1)/2 + j ; projection c_j at 216 + j.
   // Row 20 of the bordered factor is z = L^-1 c, so quad = q - z'z (null_gp.py:345-358).
-  if (tid < LK_TS * 4) {
-    const int s = tid >> 2;       // sample of this thread quad
-    const int t = tid & 3;
+  {
+    const int s = tid / LK_EP_THREADS;   // sample of this thread group (64 samples x 8 threads = 512)
+    const int t = tid % LK_EP_THREADS;
     double* Es = E + s;
     auto at = [&](int i, int j) -> double& {  // element (i,j), i >= j, i <= 20
       const int col = (i < LK_K) ? (i * (i + 1) / 2 + j) : (LK_PROJ_COL0 + j);
@@ -459,14 +466,14 @@ sample_likelihood_kernel(const LikelihoodSpectrum* __restrict__ specs) {
     };
     double logdet_prod = 1.0, logdet = 0.0, zz = 0.0;
     for (int j = 0; j < LK_K; ++j) {
-      // pivot (all four threads compute it redundantly)
+      // pivot (all eight threads compute it redundantly)
       double piv = at(j, j) + 1.0;  // + I (null_gp.py:341)
       for (int k = 0; k < j; ++k) { const double l = at(j, k); piv = fma(-l, l, piv); }
       logdet_prod *= piv;
       if ((j % 5) == 4) { logdet += log(logdet_prod); logdet_prod = 1.0; }
       const double inv = 1.0 / sqrt(piv);
-      // rows j+1 .. 20 of column j, interleaved over the quad
-      for (int i = j + 1 + t; i <= LK_K; i += 4) {
+      // rows j+1 .. 20 of column j, interleaved over the group
+      for (int i = j + 1 + t; i <= LK_K; i += LK_EP_THREADS) {
         double x = at(i, j);
         for (int k = 0; k < j; ++k) x = fma(-at(i, k), at(j, k), x);
         x *= inv;
@@ -475,9 +482,10 @@ sample_likelihood_kernel(const LikelihoodSpectrum* __restrict__ specs) {
       }
       __syncwarp();
     }
-    // row 20 moved round the quad from column to column; sum the partial z'z
+    // row 20 moved round the group from column to column; sum the partial z'z
     zz += __shfl_xor_sync(0xffffffffu, zz, 1);
     zz += __shfl_xor_sync(0xffffffffu, zz, 2);
+    zz += __shfl_xor_sync(0xffffffffu, zz, 4);
     if (t == 0 && tile_s0 + s < sp.num_samples) {
       const double quad = s_sums[s * 2] - zz;
       const double log_det = s_sums[s * 2 + 1] + logdet;  // sum log d + 2 sum log L_ii
