@@ -453,42 +453,81 @@ sample_likelihood_kernel(const LikelihoodSpectrum* __restrict__ specs) {
   }
   __syncthreads();
 
-  // ---- Cholesky of the bordered matrix [[B, c], [c', q]] : 8 threads per sample ------------
-  // E col layout: pair (i,j) at i(i+1)/2 + j ; projection c_j at 216 + j.
-  // Row 20 of the bordered factor is z = L^-1 c, so quad = q - z'z (null_gp.py:345-358).
+  // ---- Cholesky of the bordered matrix [[B, c], [c', q]] : 8 threads per sample, in registers --------------
+  // E col layout: pair (i,j) at i(i+1)/2 + j ; projection c_j at 216 + j.  Row 20 of the bordered factor is
+  // z = L^-1 c, so quad = q - z'z (null_gp.py:345-358).  Thread t of a sample's group owns rows t, t + 8 and
+  // t + 16 of the lower triangle (row 20 = the projection row) in three register arrays with compile-time
+  // indices; column j needs the finished entries of row j, which its owner broadcasts by shuffles, and every
+  // dot product is two independent FMA chains.  (The first version walked the matrix in shared memory with
+  // two loads per FMA and took 13 % of the kernel with the tensor pipe idle.)
   {
-    const int s = tid / LK_EP_THREADS;   // sample of this thread group (64 samples x 8 threads = 512)
-    const int t = tid % LK_EP_THREADS;
-    double* Es = E + s;
-    auto at = [&](int i, int j) -> double& {  // element (i,j), i >= j, i <= 20
-      const int col = (i < LK_K) ? (i * (i + 1) / 2 + j) : (LK_PROJ_COL0 + j);
-      return Es[col * LK_EP_STRIDE];
-    };
-    double logdet_prod = 1.0, logdet = 0.0, zz = 0.0;
-    for (int j = 0; j < LK_K; ++j) {
-      // pivot (all eight threads compute it redundantly)
-      double piv = at(j, j) + 1.0;  // + I (null_gp.py:341)
-      for (int k = 0; k < j; ++k) { const double l = at(j, k); piv = fma(-l, l, piv); }
-      logdet_prod *= piv;
-      if ((j % 5) == 4) { logdet += log(logdet_prod); logdet_prod = 1.0; }
-      const double inv = 1.0 / sqrt(piv);
-      // rows j+1 .. 20 of column j, interleaved over the group
-      for (int i = j + 1 + t; i <= LK_K; i += LK_EP_THREADS) {
-        double x = at(i, j);
-        for (int k = 0; k < j; ++k) x = fma(-at(i, k), at(j, k), x);
-        x *= inv;
-        at(i, j) = x;
-        if (i == LK_K) zz = fma(x, x, zz);
-      }
-      __syncwarp();
+    const int s = tid >> 3;          // sample of this thread group (64 samples x 8 threads = 512)
+    const int t = tid & 7;
+    const int gbase = lane & ~7;
+    const double* Es = E + s;
+    double r0[8], r1[16], r2[20];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) r0[k] = k <= t ? Es[(t * (t + 1) / 2 + k) * LK_EP_STRIDE] + (k == t ? 1.0 : 0.0) : 0.0;
+#pragma unroll
+    for (int k = 0; k < 16; ++k) {
+      const int i = t + 8;
+      r1[k] = k <= i ? Es[(i * (i + 1) / 2 + k) * LK_EP_STRIDE] + (k == i ? 1.0 : 0.0) : 0.0;
     }
-    // row 20 moved round the group from column to column; sum the partial z'z
-    zz += __shfl_xor_sync(0xffffffffu, zz, 1);
-    zz += __shfl_xor_sync(0xffffffffu, zz, 2);
-    zz += __shfl_xor_sync(0xffffffffu, zz, 4);
-    if (t == 0 && tile_s0 + s < sp.num_samples) {
-      const double quad = s_sums[s * 2] - zz;
-      const double log_det = s_sums[s * 2 + 1] + logdet;  // sum log d + 2 sum log L_ii
+#pragma unroll
+    for (int k = 0; k < 20; ++k) {
+      const int i = t + 16;  // rows 16..19 of B, row 20 = c, rows 21..23 do not exist
+      double val = 0.0;
+      if (i < LK_K) { if (k <= i) val = Es[(i * (i + 1) / 2 + k) * LK_EP_STRIDE] + (k == i ? 1.0 : 0.0); }
+      else if (i == LK_K) val = Es[(LK_PROJ_COL0 + k) * LK_EP_STRIDE];
+      r2[k] = val;
+    }
+    double piv_prod = 1.0;
+#pragma unroll
+    for (int j = 0; j < LK_K; ++j) {
+      const int owner = gbase + (j & 7);
+      // finished entries of row j (k < j), from its owner
+      double Lj[LK_K];
+#pragma unroll
+      for (int k = 0; k < j; ++k)
+        Lj[k] = __shfl_sync(0xffffffffu, j < 8 ? r0[k < 8 ? k : 0] : j < 16 ? r1[k < 16 ? k : 0] : r2[k], owner);
+      // x_q = A[i_q][j] - sum_k L[i_q][k] L[j][k] for the rows of every slot that reaches column j
+      double x0 = 0.0, x1 = 0.0, x2 = r2[j];
+      if (j < 8) {
+        double e0 = r0[j], e1 = 0.0;
+#pragma unroll
+        for (int k = 0; k + 1 < j; k += 2) { e0 = fma(-r0[k], Lj[k], e0); e1 = fma(-r0[k + 1], Lj[k + 1], e1); }
+        if (j & 1) e0 = fma(-r0[j - 1], Lj[j - 1], e0);
+        x0 = e0 + e1;
+      }
+      if (j < 16) {
+        double e0 = r1[j], e1 = 0.0;
+#pragma unroll
+        for (int k = 0; k + 1 < j; k += 2) { e0 = fma(-r1[k], Lj[k], e0); e1 = fma(-r1[k + 1], Lj[k + 1], e1); }
+        if (j & 1) e0 = fma(-r1[j - 1], Lj[j - 1], e0);
+        x1 = e0 + e1;
+      }
+      {
+        double e0 = x2, e1 = 0.0;
+#pragma unroll
+        for (int k = 0; k + 1 < j; k += 2) { e0 = fma(-r2[k], Lj[k], e0); e1 = fma(-r2[k + 1], Lj[k + 1], e1); }
+        if (j & 1) e0 = fma(-r2[j - 1], Lj[j - 1], e0);
+        x2 = e0 + e1;
+      }
+      // the pivot is the x of row j itself
+      const double piv = __shfl_sync(0xffffffffu, j < 8 ? x0 : j < 16 ? x1 : x2, owner);
+      piv_prod *= piv;
+      const double inv = rsqrt(piv);
+      if (j < 8) r0[j] = x0 * inv;    // rows below j become column j of L (the pivot row's own entry is not used again)
+      if (j < 16) r1[j] = x1 * inv;
+      r2[j] = x2 * inv;
+    }
+    // z'z on the owner of row 20 (t = 4, third slot)
+    if (t == 4 && tile_s0 + s < sp.num_samples) {
+      double zz0 = 0.0, zz1 = 0.0;
+#pragma unroll
+      for (int k = 0; k < LK_K; k += 2) { zz0 = fma(r2[k], r2[k], zz0); zz1 = fma(r2[k + 1], r2[k + 1], zz1); }
+      const double quad = s_sums[s * 2] - (zz0 + zz1);
+      const double log_det = s_sums[s * 2 + 1] + log(piv_prod);  // sum log d + 2 sum log L_ii
       sp.out[tile_s0 + s] = -0.5 * (quad + log_det + (double)n * LK_LOG_2PI);
     }
   }
