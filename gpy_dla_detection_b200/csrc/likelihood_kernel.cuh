@@ -298,11 +298,14 @@ sample_likelihood_kernel(const LikelihoodSpectrum* __restrict__ specs) {
   };
 
   // phase A: W/G tiles of `panel`.  Branch-free over the four elements of a thread so that their
-  // dependent chains (load, products, reciprocal, ...) interleave; validity is a select at the end.
+  // dependent chains (load, products, reciprocal, ...) interleave.  Pixels beyond n are neutralised once per
+  // thread (a = 0, y = mu = omega2 = 0, v = 1  =>  w = g = 0, d = 1); samples beyond num_samples (last
+  // tile of a spectrum) compute on row 0 and are simply never written out - no per-element selects.
   auto produce = [&](int panel) {
     const int p = panel * LK_KC + lane;
     const bool pv = p < n;
-    const double yp = s_pix[lane], mup = s_pix[LK_KC + lane], omp = s_pix[2 * LK_KC + lane], vp = s_pix[3 * LK_KC + lane];
+    const double yp = pv ? s_pix[lane] : 0.0, mup = pv ? s_pix[LK_KC + lane] : 0.0;
+    const double omp = pv ? s_pix[2 * LK_KC + lane] : 0.0, vp = pv ? s_pix[3 * LK_KC + lane] : 1.0;
     double a[LK_EPT];
 #pragma unroll
     for (int e = 0; e < LK_EPT; ++e) a[e] = s_raw0[(warp + LK_WARPS * e) * LK_KC + lane];
@@ -318,20 +321,24 @@ sample_likelihood_kernel(const LikelihoodSpectrum* __restrict__ specs) {
         for (int r = 2; r < num_rows; ++r)
           a[e] = a[e] * sp.cache[(size_t)s_rows[r * LK_TS + warp + LK_WARPS * e] * sp.ld + pc];
     }
+    if (sp.prod_out && pv) {
+#pragma unroll
+      for (int e = 0; e < LK_EPT; ++e)
+        if ((live >> e) & 1u) sp.prod_out[(size_t)(tile_s0 + warp + LK_WARPS * e) * sp.ld + p] = a[e];
+    }
 #pragma unroll
     for (int e = 0; e < LK_EPT; ++e) {
       const int s = warp + LK_WARPS * e;
-      const bool ok = pv && ((live >> e) & 1u);
-      if (ok && sp.prod_out) sp.prod_out[(size_t)(tile_s0 + s) * sp.ld + p] = a[e];
-      const double a2 = a[e] * a[e];
+      const double ae = pv ? a[e] : 0.0;      // pad columns of the profile rows hold no data
+      const double a2 = ae * ae;
       const double d = fma(omp, a2, vp);      // dla_omega2 + v
       const double inv = fast_rcp(d);
-      const double r = fma(-mup, a[e], yp);   // y - dla_mu
+      const double r = fma(-mup, ae, yp);     // y - dla_mu
       const double t = r * inv;
-      s_W[s * LK_WSTRIDE + lane] = ok ? a2 * inv : 0.0;
-      s_G[s * LK_WSTRIDE + lane] = ok ? a[e] * t : 0.0;
-      q_acc[e] = ok ? fma(r, t, q_acc[e]) : q_acc[e];
-      dprod[e] = ok ? dprod[e] * d : dprod[e];
+      s_W[s * LK_WSTRIDE + lane] = a2 * inv;
+      s_G[s * LK_WSTRIDE + lane] = ae * t;
+      q_acc[e] = fma(r, t, q_acc[e]);
+      dprod[e] *= d;
     }
   };
 
