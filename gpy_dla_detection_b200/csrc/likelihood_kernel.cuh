@@ -362,7 +362,7 @@ sample_likelihood_kernel(const LikelihoodSpectrum* __restrict__ specs) {
     for (int nb = 0; nb < LK_NB_MAX; ++nb) acc[m][nb][0] = acc[m][nb][1] = 0.0;
 
   // phase B: DMMAs of `panel`
-  auto consume = [&](int panel) {
+  auto consume = [&](int panel, bool stage_next) {
     const int pstage = panel & (LK_PSTAGES - 1);
     const double* Ps = s_main + pstage * LK_PANEL_DOUBLES;
     mbar_wait(bar_base + 8u * pstage, (panel / LK_PSTAGES) & 1);  // basis panel landed
@@ -373,6 +373,9 @@ sample_likelihood_kernel(const LikelihoodSpectrum* __restrict__ specs) {
     const double* brow = Ps + tig * LK_PSTRIDE + first * 8 + grp;
 #pragma unroll
     for (int kb = 0; kb < LK_KC / 4; ++kb) {
+      // the cp.async requests of the next panel go out after the first DMMAs, so that their address
+      // arithmetic runs while the tensor pipe already has work queued
+      if (kb == 1 && stage_next) stage_panel(panel + 1);
       double a[LK_MB];
 #pragma unroll
       for (int m = 0; m < LK_MB; ++m) a[m] = arow[m * 8 * LK_WSTRIDE + kb * 4];
@@ -417,8 +420,7 @@ sample_likelihood_kernel(const LikelihoodSpectrum* __restrict__ specs) {
     if (tid == 0 && panel + 1 < npanels) issue_panel(panel + 1);  // its stage was drained by phase B of panel - 1
     produce(panel);
     __syncthreads();                                              // W/G complete, staged inputs consumed
-    if (panel + 1 < npanels) stage_panel(panel + 1);              // in flight underneath the DMMAs
-    consume(panel);
+    consume(panel, panel + 1 < npanels);                          // stages the next panel's inputs underneath the DMMAs
     if ((panel & 3) == 3) renorm();
     cp_async_wait_all();
     __syncthreads();                                              // W/G and the basis stage are free, inputs staged
