@@ -279,9 +279,11 @@ sample_likelihood_kernel(const LikelihoodSpectrum* __restrict__ specs) {
   // stage the inputs of `panel` in shared memory with cp.async: issued at the start of phase B, so the
   // copies fly underneath the DMMAs and no register is held for them (a register prefetch of 4 elements
   // x 2 factors spilled, and the spill store waited for the load)
-  auto stage_panel = [&](int panel) {
+  // `nthreads` threads with rank `r` (all 512 in the prologue; in the main loop the 8 warps that own
+  // only 7 column blocks, i.e. the ones with 1/8 less DMMA work)
+  auto stage_panel = [&](int panel, int r, int nthreads) {
     const int p0 = panel * LK_KC;
-    for (int idx = tid; idx < LK_TS * LK_KC / 2; idx += LK_THREADS) {  // 16-byte chunks: 16 per sample row
+    for (int idx = r; idx < LK_TS * LK_KC / 2; idx += nthreads) {  // 16-byte chunks: 16 per sample row
       const int s = idx >> 4, j = (idx & 15) * 2;
       const int p = p0 + j;
       const int ok = p < sp.ld ? 16 : 0;  // rows are padded to ld (multiple of 4): zero-fill beyond
@@ -289,8 +291,8 @@ sample_likelihood_kernel(const LikelihoodSpectrum* __restrict__ specs) {
       cp_async16_zfill(s_raw0 + s * LK_KC + j, sp.base0 + (size_t)s_rows[s] * sp.ld + off, ok);
       if (two_rows) cp_async16_zfill(s_raw1 + s * LK_KC + j, sp.cache + (size_t)s_rows[LK_TS + s] * sp.ld + off, ok);
     }
-    if (tid < 4 * LK_KC) {
-      const int arr = tid >> 5, j = tid & 31;
+    if (r < 4 * LK_KC) {
+      const int arr = r >> 5, j = r & 31;
       const double* src = arr == 0 ? sp.y : arr == 1 ? sp.mu : arr == 2 ? sp.omega2 : sp.v;
       cp_async8(s_pix + arr * LK_KC + j, src + min(p0 + j, n - 1));
     }
@@ -355,6 +357,7 @@ sample_likelihood_kernel(const LikelihoodSpectrum* __restrict__ specs) {
   const int first = !odd ? (cq == 0 ? 0 : cq == 1 ? 8 : cq == 2 ? 15 : 23) : (cq == 0 ? 0 : cq == 1 ? 7 : cq == 2 ? 15 : 22);
   const bool has_eighth = ((cq + (odd ? 1 : 0)) & 1) == 0;
   const bool g4 = first + 4 >= LK_NBLK_PAIR, g5 = first + 5 >= LK_NBLK_PAIR;
+  const int stage_rank = (rq * 2 + (cq >> 1)) * 32 + lane;  // rank among the 256 threads of the 7-block warps
   double acc[LK_MB][LK_NB_MAX][2];
 #pragma unroll
   for (int m = 0; m < LK_MB; ++m)
@@ -374,8 +377,9 @@ sample_likelihood_kernel(const LikelihoodSpectrum* __restrict__ specs) {
 #pragma unroll
     for (int kb = 0; kb < LK_KC / 4; ++kb) {
       // the cp.async requests of the next panel go out after the first DMMAs, so that their address
-      // arithmetic runs while the tensor pipe already has work queued
-      if (kb == 1 && stage_next) stage_panel(panel + 1);
+      // arithmetic runs while the tensor pipe already has work queued; they are issued by the warps that
+      // own 7 column blocks, which otherwise idle at the barrier while the 8-block warps finish
+      if (kb == 1 && stage_next && !has_eighth) stage_panel(panel + 1, stage_rank, (LK_WARPS / 2) * 32);
       double a[LK_MB];
 #pragma unroll
       for (int m = 0; m < LK_MB; ++m) a[m] = arow[m * 8 * LK_WSTRIDE + kb * 4];
@@ -413,7 +417,7 @@ sample_likelihood_kernel(const LikelihoodSpectrum* __restrict__ specs) {
   };
 
   // ---- main loop: phase A | barrier | phase B | barrier --------------------------------------------------
-  stage_panel(0);
+  stage_panel(0, tid, LK_THREADS);
   cp_async_wait_all();
   __syncthreads();
   for (int panel = 0; panel < npanels; ++panel) {
