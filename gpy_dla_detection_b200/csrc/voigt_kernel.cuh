@@ -18,6 +18,32 @@ __device__ __constant__ double c_damping_y[LYMAN_NUM_LINES] = LYMAN_DAMPING_Y;
 __device__ __constant__ double c_coef[LYMAN_NUM_LINES] = LYMAN_NEG_LEADING_OVER_NORM;
 __device__ __constant__ double c_instrument[2 * INSTRUMENT_WIDTH + 1] = INSTRUMENT_PROFILE;
 
+// exp(x) for the profile, x = N_HI * sum of line terms (<= 0).  Same structure as any exp - argument
+// reduction x = i ln2 + r by the magic-number rint, degree-13 Taylor polynomial on |r| <= ln2 / 2
+// (truncation 4e-18 relative), scaling by 2^i in the exponent field - but with the coefficients in the
+// constant bank, where a DFMA reads them as operands: the library routine materialises every
+// coefficient with two uniform-register moves, a quarter of the instructions of the profile's inner
+// loop.  <= 2 ulp from the correctly rounded value.  Outside [-708, 700] (deeply saturated cores,
+// non-finite input) the library routine handles underflow, overflow and NaN.
+__device__ __constant__ double c_exp_taylor[14] = {
+    1.0 / 6227020800.0, 1.0 / 479001600.0, 1.0 / 39916800.0, 1.0 / 3628800.0, 1.0 / 362880.0, 1.0 / 40320.0,
+    1.0 / 5040.0,       1.0 / 720.0,       1.0 / 120.0,      1.0 / 24.0,      1.0 / 6.0,      0.5,
+    1.0,                1.0};
+__device__ __constant__ double c_exp_consts[4] = {1.4426950408889634074, 6.93147180559945286227e-01,
+                                                  2.31904681384629955842e-17, 6755399441055744.0};
+__device__ __forceinline__ double profile_exp(double x) {
+  if (!(x >= -708.0 && x <= 700.0)) return exp(x);
+  double t = fma(x, c_exp_consts[0], c_exp_consts[3]);
+  const int i = __double2loint(t);
+  t -= c_exp_consts[3];
+  double r = fma(-t, c_exp_consts[1], x);
+  r = fma(-t, c_exp_consts[2], r);
+  double p = c_exp_taylor[0];
+#pragma unroll
+  for (int k = 1; k < 14; ++k) p = fma(p, r, c_exp_taylor[k]);
+  return __hiloint2double(__double2hiint(p) + (i << 20), __double2loint(p));
+}
+
 // One absorption grid (one spectrum): what the profile kernel needs to know.
 struct AbsorptionGrid {
   const double* wl;    // n_in wavelengths the raw profile is evaluated on (padded or unmasked grid)
@@ -70,14 +96,14 @@ __device__ __forceinline__ double raw_profile_at(double lam, const double* mult,
         const double h = dla_faddeeva_far(dla_wing_rcp(ax * ax), y, y * y);
         total += c_coef[l] * h;  // finite by construction: nansum has nothing to skip
       }
-      return exp(nhi * total);
+      return profile_exp(nhi * total);
     }
 #pragma unroll
     for (int l = 0; l < NL; ++l) {
       const double term = c_coef[l] * dla_faddeeva_re(x[l], c_damping_y[l]);
       if (!isnan(term)) total += term;  // np.nansum
     }
-    return exp(nhi * total);
+    return profile_exp(nhi * total);
   }
   for (int l = 0; l < nl; ++l) {
     const double vel = __dsub_rn(__dmul_rn(lam, mult[l]), LYMAN_C_CGS);
@@ -87,7 +113,7 @@ __device__ __forceinline__ double raw_profile_at(double lam, const double* mult,
     const double term = c_coef[l] * h;
     if (!isnan(term)) total += term;  // np.nansum
   }
-  return exp(nhi * total);
+  return profile_exp(nhi * total);
 }
 
 constexpr int VG_WARPS = 8;  // samples per CTA
@@ -96,7 +122,9 @@ constexpr int VG_WARPS = 8;  // samples per CTA
 template <int NL>
 __global__ void __launch_bounds__(VG_WARPS * 32)
 voigt_profile_kernel(const AbsorptionGrid* __restrict__ grids, int num_lines, int broadening) {
-  __shared__ double s_ring[VG_WARPS][2][32];
+  // ring of raw chunks: even chunks at [0,32) and again at [64,96), odd chunks at [32,64): the 7-tap
+  // window of an output pixel is contiguous whatever the parity, so the taps are immediate offsets
+  __shared__ double s_ring[VG_WARPS][96];
   __shared__ double s_mult[VG_WARPS][32];
   const AbsorptionGrid g = grids[blockIdx.y];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -124,11 +152,13 @@ voigt_profile_kernel(const AbsorptionGrid* __restrict__ grids, int num_lines, in
   // np.convolve(raw, profile, 'valid')[u] = sum_k raw[u+k] * profile[6-k], u < n_u = n_in - 6
   const int n_u = g.n_in - 2 * INSTRUMENT_WIDTH;
   const int nchunks = (g.n_in + 31) >> 5;
-  double (*ring)[32] = s_ring[warp];
+  double* ring = s_ring[warp];
   for (int j = 0; j <= nchunks; ++j) {
     if (j < nchunks) {
       const int p = (j << 5) + lane;
-      ring[j & 1][lane] = raw_profile_at<NL>(g.wl[min(p, g.n_in - 1)], mult, nhi, num_lines);  // tail lanes: unused copies
+      const double rawv = raw_profile_at<NL>(g.wl[min(p, g.n_in - 1)], mult, nhi, num_lines);  // tail lanes: unused copies
+      ring[((j & 1) << 5) + lane] = rawv;
+      if ((j & 1) == 0) ring[64 + lane] = rawv;
     }
     __syncwarp();
     if (j >= 1) {
@@ -136,12 +166,10 @@ voigt_profile_kernel(const AbsorptionGrid* __restrict__ grids, int num_lines, in
       if (u < n_u) {
         const int q = g.qmap[u];
         if (q >= 0) {
+          const double* win = ring + (((j - 1) & 1) << 5) + lane;  // elements u .. u + 6
           double acc = 0.0;
 #pragma unroll
-          for (int k = 0; k <= 2 * INSTRUMENT_WIDTH; ++k) {
-            const int t = lane + k;  // element u + k lives in chunk j-1 (t < 32) or chunk j
-            acc = fma(ring[(j - 1 + (t >> 5)) & 1][t & 31], c_instrument[2 * INSTRUMENT_WIDTH - k], acc);
-          }
+          for (int k = 0; k <= 2 * INSTRUMENT_WIDTH; ++k) acc = fma(win[k], c_instrument[2 * INSTRUMENT_WIDTH - k], acc);
           out[q] = acc;
         }
       }
