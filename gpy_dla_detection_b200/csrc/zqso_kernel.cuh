@@ -148,7 +148,7 @@ __device__ __forceinline__ int zq_bound_rest(const double* X, double opz, int a,
 
 // grid = (ceil(S / 8), num_spectra), block = 256, dynamic smem = 8 * per_warp doubles,
 // per_warp = max(norm_cap, 24 * 25); norm_cap = power of two >= pixels in any normalisation window
-__global__ void __launch_bounds__(ZQ_WARPS * 32)
+__global__ void __launch_bounds__(ZQ_WARPS * 32, 3)
 zqso_likelihood_kernel(const ZqsoSpectrum* __restrict__ spectra, const double* __restrict__ z_samples, int S,
                        ZqsoModelDev model, ZqsoParamsDev prm, int norm_cap, int per_warp,
                        double* __restrict__ out /* [num_spectra][S] */) {
