@@ -34,7 +34,6 @@
 // HBM sees only the profile rows (read) and one double per sample (written).
 #pragma once
 #include <stdint.h>
-#include <type_traits>
 
 namespace dla {
 
@@ -52,7 +51,6 @@ constexpr int LK_WARPS = 16;
 constexpr int LK_THREADS = LK_WARPS * 32;        // 512
 constexpr int LK_PSTAGES = 2;                    // basis-panel ring (TMA)
 constexpr int LK_EP_STRIDE = LK_TS + 1;          // epilogue smem: [col][sample], stride 65
-constexpr int LK_EP_THREADS = 8;                 // threads per sample in the Cholesky phase
 constexpr int LK_MAX_ROWS = 8;                   // max absorbers multiplied per sample (max_dlas <= 8)
 constexpr int LK_MB = 2;                         // DMMA row blocks per warp (16 samples)
 constexpr int LK_NB_MAX = 8;                     // DMMA column blocks per warp (7 or 8)
@@ -129,9 +127,6 @@ __device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double
 // ---- mbarrier + TMA bulk copy -----------------------------------------------------------------------
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
 __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
