@@ -323,20 +323,41 @@ sample_likelihood_kernel(const LikelihoodSpectrum* __restrict__ specs) {
       for (int e = 0; e < LK_EPT; ++e)
         if ((live >> e) & 1u) sp.prod_out[(size_t)(tile_s0 + warp + LK_WARPS * e) * sp.ld + p] = a[e];
     }
+    // the four elements advance in lock step (one loop per operation): four independent dependency
+    // chains in flight instead of one after the other
+    double a2[LK_EPT], d[LK_EPT], r0[LK_EPT], er[LK_EPT], inv[LK_EPT], res[LK_EPT], t[LK_EPT];
+#pragma unroll
+    for (int e = 0; e < LK_EPT; ++e) a[e] = pv ? a[e] : 0.0;  // pad columns of the profile rows hold no data
+#pragma unroll
+    for (int e = 0; e < LK_EPT; ++e) a2[e] = a[e] * a[e];
+#pragma unroll
+    for (int e = 0; e < LK_EPT; ++e) d[e] = fma(omp, a2[e], vp);          // dla_omega2 + v
+#pragma unroll
+    for (int e = 0; e < LK_EPT; ++e) asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r0[e]) : "d"(d[e]));
+#pragma unroll
+    for (int e = 0; e < LK_EPT; ++e) res[e] = fma(-mup, a[e], yp);        // y - dla_mu
+#pragma unroll
+    for (int e = 0; e < LK_EPT; ++e) er[e] = fma(-d[e], r0[e], 1.0);
+#pragma unroll
+    for (int e = 0; e < LK_EPT; ++e) inv[e] = fma(r0[e], er[e], r0[e]);
+#pragma unroll
+    for (int e = 0; e < LK_EPT; ++e) er[e] = fma(-d[e], inv[e], 1.0);
+#pragma unroll
+    for (int e = 0; e < LK_EPT; ++e) inv[e] = fma(inv[e], er[e], inv[e]);
+#pragma unroll
+    for (int e = 0; e < LK_EPT; ++e) inv[e] = (d[e] > 1e-290 && d[e] < 1e290) ? inv[e] : r0[e];  // see fast_rcp
+#pragma unroll
+    for (int e = 0; e < LK_EPT; ++e) t[e] = res[e] * inv[e];
 #pragma unroll
     for (int e = 0; e < LK_EPT; ++e) {
       const int s = warp + LK_WARPS * e;
-      const double ae = pv ? a[e] : 0.0;      // pad columns of the profile rows hold no data
-      const double a2 = ae * ae;
-      const double d = fma(omp, a2, vp);      // dla_omega2 + v
-      const double inv = fast_rcp(d);
-      const double r = fma(-mup, ae, yp);     // y - dla_mu
-      const double t = r * inv;
-      s_W[s * LK_WSTRIDE + lane] = a2 * inv;
-      s_G[s * LK_WSTRIDE + lane] = ae * t;
-      q_acc[e] = fma(r, t, q_acc[e]);
-      dprod[e] *= d;
+      s_W[s * LK_WSTRIDE + lane] = a2[e] * inv[e];
+      s_G[s * LK_WSTRIDE + lane] = a[e] * t[e];
     }
+#pragma unroll
+    for (int e = 0; e < LK_EPT; ++e) q_acc[e] = fma(res[e], t[e], q_acc[e]);
+#pragma unroll
+    for (int e = 0; e < LK_EPT; ++e) dprod[e] *= d[e];
   };
 
   // ---- MMA role: warp (rq, cq) owns samples 16 rq .. 16 rq + 15 and 7 or 8 column blocks -----------
