@@ -65,6 +65,7 @@ struct dla_catalogue {
   const dla_model* model = nullptr;
   dla_params params;
   int S = 0, max_dlas = 0, B = 0, keep = 0;
+  bool paired_offsets = false;  // DLA and subDLA samples share their redshift offsets: one line-sum evaluation for both
   // constants
   DevBuf<double> dla_offsets, dla_log_nhi, sub_offsets, nhi_all /* [dla_nhi ; sub_nhi] */, uniforms;
   // staged inputs
@@ -121,6 +122,7 @@ extern "C" int dla_catalogue_create(const dla_model* model, const dla_params* pa
   cat->max_dlas = max_dlas;
   cat->B = config->batch_spectra > 0 ? config->batch_spectra : 64;
   cat->keep = config->keep_sample_likelihoods;
+  cat->paired_offsets = memcmp(dla_offset_samples, sub_offset_samples, sizeof(double) * (size_t)S) == 0;
   DLA_CUDA(cat->dla_offsets.alloc(S));
   DLA_CUDA(cat->dla_log_nhi.alloc(S));
   DLA_CUDA(cat->sub_offsets.alloc(S));
@@ -357,6 +359,7 @@ extern "C" int dla_catalogue_run_staged(dla_catalogue* cat, dla_catalogue_output
       g.num_samples = usable ? 2 * S : 0;
       g.z = cat->z_samples.p + (size_t)b * 2 * S;
       g.nhi = cat->nhi_all.p;
+      g.pair_offset = cat->paired_offsets ? S : 0;
       h_grid[b] = g;
       for (int level = 0; level < md; ++level) {
         LikelihoodSpectrum d;
@@ -488,7 +491,9 @@ extern "C" int dla_catalogue_run_staged(dla_catalogue* cat, dla_catalogue_output
       build_qmap_kernel<<<nb, 256, 0, rt.stream>>>(cat->grid_desc.p, cat->params.broadening);
       DLA_LAUNCHED();
       DLA_CUDA(cudaEventRecord(e_v0, rt.stream));
-      if ((rc = launch_voigt_grids(cat->grid_desc.p, 2 * S, nb, cat->params.num_lines, cat->params.broadening))) return rc;
+      if ((rc = launch_voigt_grids(cat->grid_desc.p, cat->paired_offsets ? S : 2 * S, nb, cat->params.num_lines,
+                                   cat->params.broadening)))
+        return rc;
       DLA_CUDA(cudaEventRecord(e_v1, rt.stream));
     }
     // levels

@@ -197,6 +197,7 @@ static int launch_voigt(dla_spectrum* sp, const double* d_z, const double* d_nhi
   g.num_samples = num_samples;
   g.z = d_z;
   g.nhi = d_nhi;
+  g.pair_offset = 0;
   const int n_u = sp->broadening ? sp->n_abs - 2 * INSTRUMENT_WIDTH : sp->n_abs;
   DLA_CUDA(sp->qmap.ensure(std::max(n_u, 1)));
   g.qmap = sp->qmap.p;

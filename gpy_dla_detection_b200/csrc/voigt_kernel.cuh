@@ -56,6 +56,10 @@ struct AbsorptionGrid {
   int num_samples;     // rows to produce for this spectrum
   const double* z;     // num_samples absorber redshifts
   const double* nhi;   // num_samples column densities
+  int pair_offset;     // 0, or S when samples i and i + S share their redshift (the reference's DLA and subDLA
+                       // samples use the same offset_samples, set_lls_parameters.m:22 / subdla_samples.py:87):
+                       // only the first S samples are launched, each warp evaluates the line sums once
+                       // and writes rows i and i + S with the two column densities
 };
 
 // qmap = inverse of uidx; one CTA per spectrum
@@ -68,13 +72,14 @@ __global__ void __launch_bounds__(256) build_qmap_kernel(const AbsorptionGrid* _
   for (int q = threadIdx.x; q < g.n_out; q += blockDim.x) qmap[g.uidx[q]] = q;
 }
 
-// raw profile value at one wavelength (voigt.py:296-307); NL > 0: compile-time number of lines.
+// sum over the lines of -lc_l V_l(lambda) at one wavelength (voigt.py:296-307); the raw profile is
+// exp(N_HI * sum).  NL > 0: compile-time number of lines.
 // Must be called by all 32 lanes (warp vote): when every lane is in the far wing (|x| >= 64) of
 // every line - more than 9 chunks in 10 - the lines are evaluated in straight-line code; the
 // arithmetic is the same sequence of operations as the general path, so a value does not depend on
 // which path produced it.
 template <int NL>
-__device__ __forceinline__ double raw_profile_at(double lam, const double* mult, double nhi, int num_lines) {
+__device__ __forceinline__ double line_sum_at(double lam, const double* mult, int num_lines) {
   double total = 0.0;
   const int nl = NL > 0 ? NL : num_lines;
   if (NL > 0) {
@@ -96,14 +101,14 @@ __device__ __forceinline__ double raw_profile_at(double lam, const double* mult,
         const double h = dla_faddeeva_far(dla_wing_rcp(ax * ax), y, y * y);
         total += c_coef[l] * h;  // finite by construction: nansum has nothing to skip
       }
-      return profile_exp(nhi * total);
+      return total;
     }
 #pragma unroll
     for (int l = 0; l < NL; ++l) {
       const double term = c_coef[l] * dla_faddeeva_re(x[l], c_damping_y[l]);
       if (!isnan(term)) total += term;  // np.nansum
     }
-    return profile_exp(nhi * total);
+    return total;
   }
   for (int l = 0; l < nl; ++l) {
     const double vel = __dsub_rn(__dmul_rn(lam, mult[l]), LYMAN_C_CGS);
@@ -113,7 +118,7 @@ __device__ __forceinline__ double raw_profile_at(double lam, const double* mult,
     const double term = c_coef[l] * h;
     if (!isnan(term)) total += term;  // np.nansum
   }
-  return profile_exp(nhi * total);
+  return total;
 }
 
 constexpr int VG_WARPS = 8;  // samples per CTA
@@ -124,41 +129,54 @@ __global__ void __launch_bounds__(VG_WARPS * 32)
 voigt_profile_kernel(const AbsorptionGrid* __restrict__ grids, int num_lines, int broadening) {
   // ring of raw chunks: even chunks at [0,32) and again at [64,96), odd chunks at [32,64): the 7-tap
   // window of an output pixel is contiguous whatever the parity, so the taps are immediate offsets
-  __shared__ double s_ring[VG_WARPS][96];
+  __shared__ double s_ring[VG_WARPS][2][96];
   __shared__ double s_mult[VG_WARPS][32];
   const AbsorptionGrid g = grids[blockIdx.y];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int sample = blockIdx.x * VG_WARPS + warp;
-  if (sample >= g.num_samples) return;
+  const bool paired = g.pair_offset > 0;
+  if (sample >= (paired ? g.pair_offset : g.num_samples) || g.num_samples == 0) return;
   double* mult = s_mult[warp];
 
   const double zd = g.z[sample];
   const double nhi = g.nhi[sample];
+  const double nhi2 = paired ? g.nhi[sample + g.pair_offset] : 0.0;
   // multipliers = c / (transition_wavelengths * (1 + z_dla)) / 1e8   (voigt.py:296)
   if (lane < (NL > 0 ? NL : num_lines))
     mult[lane] = __ddiv_rn(__ddiv_rn(LYMAN_C_CGS, __dmul_rn(c_tw_cm[lane], __dadd_rn(1.0, zd))), 1e8);
   __syncwarp();
 
   double* out = g.out + (size_t)sample * g.ld;
+  double* out2 = g.out + (size_t)(sample + g.pair_offset) * g.ld;
   if (!broadening) {
     for (int p0 = 0; p0 < g.n_in; p0 += 32) {
       const int p = p0 + lane;
-      const double a = raw_profile_at<NL>(g.wl[min(p, g.n_in - 1)], mult, nhi, num_lines);
+      const double total = line_sum_at<NL>(g.wl[min(p, g.n_in - 1)], mult, num_lines);
       const int q = p < g.n_in ? g.qmap[p] : -1;
-      if (q >= 0) out[q] = a;
+      if (q >= 0) {
+        out[q] = profile_exp(nhi * total);
+        if (paired) out2[q] = profile_exp(nhi2 * total);
+      }
     }
     return;
   }
   // np.convolve(raw, profile, 'valid')[u] = sum_k raw[u+k] * profile[6-k], u < n_u = n_in - 6
   const int n_u = g.n_in - 2 * INSTRUMENT_WIDTH;
   const int nchunks = (g.n_in + 31) >> 5;
-  double* ring = s_ring[warp];
+  double* ring = s_ring[warp][0];
+  double* ring2 = s_ring[warp][1];
   for (int j = 0; j <= nchunks; ++j) {
     if (j < nchunks) {
       const int p = (j << 5) + lane;
-      const double rawv = raw_profile_at<NL>(g.wl[min(p, g.n_in - 1)], mult, nhi, num_lines);  // tail lanes: unused copies
+      const double total = line_sum_at<NL>(g.wl[min(p, g.n_in - 1)], mult, num_lines);  // tail lanes: unused copies
+      const double rawv = profile_exp(nhi * total);
       ring[((j & 1) << 5) + lane] = rawv;
       if ((j & 1) == 0) ring[64 + lane] = rawv;
+      if (paired) {
+        const double rawv2 = profile_exp(nhi2 * total);
+        ring2[((j & 1) << 5) + lane] = rawv2;
+        if ((j & 1) == 0) ring2[64 + lane] = rawv2;
+      }
     }
     __syncwarp();
     if (j >= 1) {
@@ -166,11 +184,18 @@ voigt_profile_kernel(const AbsorptionGrid* __restrict__ grids, int num_lines, in
       if (u < n_u) {
         const int q = g.qmap[u];
         if (q >= 0) {
-          const double* win = ring + (((j - 1) & 1) << 5) + lane;  // elements u .. u + 6
+          const int w0 = (((j - 1) & 1) << 5) + lane;  // elements u .. u + 6
           double acc = 0.0;
 #pragma unroll
-          for (int k = 0; k <= 2 * INSTRUMENT_WIDTH; ++k) acc = fma(win[k], c_instrument[2 * INSTRUMENT_WIDTH - k], acc);
+          for (int k = 0; k <= 2 * INSTRUMENT_WIDTH; ++k) acc = fma(ring[w0 + k], c_instrument[2 * INSTRUMENT_WIDTH - k], acc);
           out[q] = acc;
+          if (paired) {
+            double acc2 = 0.0;
+#pragma unroll
+            for (int k = 0; k <= 2 * INSTRUMENT_WIDTH; ++k)
+              acc2 = fma(ring2[w0 + k], c_instrument[2 * INSTRUMENT_WIDTH - k], acc2);
+            out2[q] = acc2;
+          }
         }
       }
     }

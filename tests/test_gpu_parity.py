@@ -515,3 +515,31 @@ def test_config4_full_lyman_series_30k_samples(gpu, O):
         W = np.exp(col - np.nanmax(col))
         W[np.isnan(W)] = 0.0
         assert np.array_equal(inds[level], O.resample_indices(W, U[level]))
+
+
+def test_catalogue_unpaired_subdla_offsets(gpu, O):
+    """
+    The reference's subDLA samples reuse the DLA redshift offsets (subdla_samples.py:87) and the profile kernel
+    then evaluates the line sums once for both; with different offsets it must fall back to separate profiles.
+    """
+    from gpy_dla_detection_b200 import synthetic
+    from gpy_dla_detection_b200.run_bayes_select import CatalogueProcessor
+    from gpy_dla_detection_b200.subdla_samples import SubDLASamplesArrays
+
+    S, md = 160, 2
+    st = H.Setup(S)
+    sub = dict(st.sub)
+    sub["offset_samples"] = np.ascontiguousarray(st.sub["offset_samples"][::-1])
+    d, _ = st.sample_objects()
+    s = SubDLASamplesArrays(st.params, st.prior, sub["offset_samples"], sub["log_nhi_samples"], sub["nhi_samples"],
+                            sub["Z_lls"], sub["Z_dla"])
+    proc = CatalogueProcessor(st.params, st.prior, st.model, d, s, md, True, batch_spectra=2)
+    z_qsos = np.array([2.6, 3.5])
+    spectra = [synthetic.make_spectrum(st.model, z, seed=200 + i) for i, z in enumerate(z_qsos)]
+    out = proc.process(*proc.pack(spectra), z_qsos, keep_samples=True)
+    for q, (z, spec) in enumerate(zip(z_qsos, spectra)):
+        ref = O.process_spectrum(st.model, st.dla, sub, st.prior.less_ind(z), *spec, float(z), md)
+        assert H.ll_err(out["sample_log_likelihoods_lls"][q], ref["sample_log_likelihoods_lls"]) < LL_RTOL
+        assert H.ll_err(out["sample_log_likelihoods_dla"][q], ref["sample_log_likelihoods_dla"]) < LL_RTOL
+        assert np.array_equal(out["base_sample_inds"][q].T, ref["base_sample_inds"])
+        assert np.max(np.abs(out["log_posteriors"][q] - ref["log_posteriors"])) < EV_ATOL
