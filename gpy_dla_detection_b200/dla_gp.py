@@ -6,6 +6,8 @@ Drop-in for the reference's DLAGP (dla_gp.py:25-472): same constructor,
 `maximum_a_posteriori`, and the attributes `sample_log_likelihoods` (S, max_dlas) and
 `base_sample_inds` (max_dlas-1, S) int32.  `run_mcmc` (emcee) is outside the hot path.
 """
+from typing import Optional
+
 import numpy as np
 
 from .set_parameters import Parameters
@@ -70,5 +72,45 @@ class DLAGP(AbsorberGP):
             MAP_log_nhi[num_dlas, : num_dlas + 1] = log_nhi[chain]
         return MAP_z_dla, MAP_log_nhi
 
-    def run_mcmc(self, *args, **kwargs):
-        raise NotImplementedError("MCMC refinement (emcee) is outside the B200 hot path; see SURVEY.md §8f")
+    def mcmc_log_posterior_args(self):
+        """The argument tuple of log_posterior_mcmc.log_posterior for this spectrum (dla_gp.py:265-287)."""
+        from scipy import stats
+        from scipy.integrate import quad
+
+        ds = self.dla_samples
+        min_z_dla = self.params.min_z_dla(self.this_wavelengths, self.z_qso)
+        max_z_dla = self.params.max_z_dla(self.this_wavelengths, self.z_qso)
+        u = stats.uniform(loc=ds.uniform_min_log_nhi, scale=ds.uniform_max_log_nhi - ds.uniform_min_log_nhi)
+
+        def unnormalized_pdf(nhi):
+            return np.exp(-1.2695 * nhi**2 + 50.863 * nhi - 509.33)
+
+        Z = quad(unnormalized_pdf, ds.fit_min_log_nhi, 25.0)[0]
+
+        def normalized_pdf(nhi):
+            return ds.alpha * (unnormalized_pdf(nhi) / Z) + (1 - ds.alpha) * u.pdf(nhi)
+
+        return (self.this_wavelengths, self.y, self.v, self.z_qso, min_z_dla, max_z_dla, ds.uniform_min_log_nhi,
+                ds.uniform_max_log_nhi, normalized_pdf, self.padded_wavelengths, self.this_mu, self.this_M,
+                self.this_omega2, self.pixel_mask, self.ind_unmasked, self.params.num_lines)
+
+    def run_mcmc(self, nwalkers: int, kth_dla: int = 1, nsamples: int = 5000, pos: Optional[np.ndarray] = None,
+                 skip_initial_state_check: bool = True):
+        """
+        emcee sampling of the 1-DLA posterior (dla_gp.py:227-309).  The walkers of a step are evaluated in one
+        device call (`vectorize=True` with log_posterior_mcmc.log_posteriors).  Needs emcee, which is not part
+        of this image.
+        """
+        import emcee  # noqa: F401  (ImportError here when the package is absent, as for the reference)
+
+        from .log_posterior_mcmc import log_posteriors
+
+        sampler = emcee.EnsembleSampler(nwalkers, kth_dla * 2, log_posteriors, args=self.mcmc_log_posterior_args(),
+                                        vectorize=True)
+        if pos is None:
+            sample_z_dlas = self._sample_z()
+            pos = np.concatenate([np.random.choice(sample_z_dlas, size=nwalkers)[:, None],
+                                  np.random.choice(self.dla_samples.log_nhi_samples, size=nwalkers)[:, None]], axis=1)
+            assert pos.shape[0] == nwalkers
+        sampler.run_mcmc(pos, nsamples, progress=True, skip_initial_state_check=skip_initial_state_check)
+        return sampler

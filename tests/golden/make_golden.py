@@ -195,7 +195,41 @@ def golden_zqso():
     print("zqso_full_S10000.npz written, reference time %.1f s, z_map %.4f" % (dt, gp.z_map))
 
 
+def golden_mcmc():
+    """log_posterior_mcmc.py free functions (the emcee target of DLAGP.run_mcmc) on one prepared spectrum."""
+    from gpy_dla_detection import log_posterior_mcmc as rm
+
+    S, z_qso, seed = 64, 3.0, 7
+    rp = RParameters(num_dla_samples=S)
+    p = Parameters(num_dla_samples=S)
+    model = synthetic.make_learned_model(0)
+    prior = synthetic.SyntheticPrior(p)
+    dla = synthetic.make_dla_sample_arrays(p)
+    wl, fl, nv, pm = synthetic.make_spectrum(model, z_qso, seed=seed)
+    margs = (model["rest_wavelengths"], model["mu"], model["M"], model["log_omega"], model["log_c_0"],
+             model["log_tau_0"], model["log_beta"])
+    gp = RDLAGP(rp, prior, ref_loader.RefDLASamples(rp, dla), *margs)
+    gp.set_data(rp.emitted_wavelengths(wl, z_qso), fl, nv, pm, z_qso, build_model=True)
+    lo, hi = rp.min_z_dla(gp.this_wavelengths, z_qso), rp.max_z_dla(gp.this_wavelengths, z_qso)
+    pdf = lambda x: 0.5 + 0.1 * (x - 20.0)  # noqa: E731  (any positive function of log N_HI)
+    args = (gp.this_wavelengths, gp.y, gp.v, z_qso, lo, hi, 20.0, 23.0, pdf, gp.padded_wavelengths, gp.this_mu, gp.this_M,
+            gp.this_omega2, gp.pixel_mask, gp.ind_unmasked, 3)
+    rng = np.random.default_rng(4)
+    thetas = np.stack([rng.uniform(lo - 0.05, hi + 0.05, 40), rng.uniform(19.8, 23.2, 40)], axis=1)
+    post = np.array([rm.log_posterior(tuple(t), *args) for t in thetas])
+    pair = rm.sample_log_likelihood_k_dlas(np.array([thetas[3, 0], thetas[5, 0]]), 10 ** np.array([20.4, 21.1]), *args[1:3],
+                                           *args[9:])
+    dmu, dM, dom = rm.this_dla_gp(np.array([thetas[3, 0]]), np.array([10**20.9]), *args[9:])
+    np.savez_compressed(os.path.join(HERE, "mcmc_golden.npz"), S=S, z_qso=z_qso, seed=seed, thetas=thetas,
+                        log_posterior=post, pair_ll=pair, this_dla_mu=dmu, this_dla_M=dM, this_dla_omega2=dom,
+                        min_z_dla=lo, max_z_dla=hi)
+    print("mcmc_golden.npz written;", int(np.isfinite(post).sum()), "of 40 thetas inside the prior")
+
+
 if __name__ == "__main__":
+    if "--only-mcmc" in sys.argv:
+        golden_mcmc()
+        sys.exit(0)
     if "--only-zqso" in sys.argv:
         golden_zqso()
         sys.exit(0)
@@ -205,5 +239,6 @@ if __name__ == "__main__":
     golden_voigt()
     golden_spectra()
     golden_zqso()
+    golden_mcmc()
     if "--no-full" not in sys.argv:
         golden_full()
