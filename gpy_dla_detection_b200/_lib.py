@@ -86,6 +86,8 @@ SIGNATURES = {
     "dla_measure_fp64_peaks": (c_int, [_dp, _dp]),
     "dla_voigt_absorption": (c_int, [_dp, c_int, c_double, c_double, c_int, c_int, _dp]),
     "dla_voigt_absorption_batch": (c_int, [_dp, c_int, _dp, _dp, c_int, c_int, c_int, _dp]),
+    "dla_voigt_lls_absorption_batch": (c_int, [_dp, c_int, _dp, _dp, c_int, c_int, c_int, _dp]),
+    "dla_spectrum_set_lls_break": (c_int, [c_void_p, c_int]),
     "dla_faddeeva_re": (c_int, [_dp, _dp, c_int, _dp]),
     "dla_effective_optical_depth": (c_int, [_dp, c_int, c_double, c_double, c_double, c_int, _dp]),
     "dla_log_mvnpdf_low_rank": (c_int, [_dp, _dp, _dp, _dp, c_int, c_int, _dp]),

@@ -360,6 +360,7 @@ extern "C" int dla_catalogue_run_staged(dla_catalogue* cat, dla_catalogue_output
       g.z = cat->z_samples.p + (size_t)b * 2 * S;
       g.nhi = cat->nhi_all.p;
       g.pair_offset = cat->paired_offsets ? S : 0;
+      g.lls_break = 0;
       h_grid[b] = g;
       for (int level = 0; level < md; ++level) {
         LikelihoodSpectrum d;

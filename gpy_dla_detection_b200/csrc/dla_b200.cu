@@ -145,6 +145,7 @@ struct dla_model {
 
 struct dla_spectrum {
   int n_raw = 0, n_u = 0, n = 0, k = 0, width = 0, broadening = 1, n_abs = 0, ld = 0;
+  int lls_break = 0;  // profiles include the Lyman-limit break (voigt_lls.py)
   double z_qso = 0.0;
   double scalars[8] = {0};
   bool from_raw = false;
@@ -198,6 +199,7 @@ static int launch_voigt(dla_spectrum* sp, const double* d_z, const double* d_nhi
   g.z = d_z;
   g.nhi = d_nhi;
   g.pair_offset = 0;
+  g.lls_break = sp->lls_break;
   const int n_u = sp->broadening ? sp->n_abs - 2 * INSTRUMENT_WIDTH : sp->n_abs;
   DLA_CUDA(sp->qmap.ensure(std::max(n_u, 1)));
   g.qmap = sp->qmap.p;
@@ -315,8 +317,27 @@ extern "C" int dla_measure_fp64_peaks(double* dfma_tflops, double* dmma_tflops) 
 // ------------------------------------------------------------------------------------------
 // a1: voigt
 // ------------------------------------------------------------------------------------------
+static int voigt_batch_impl(const double* wavelengths, int n_in, const double* nhis, const double* z_dlas, int S,
+                            int num_lines, int broadening, int lls_break, double* out);
+
 extern "C" int dla_voigt_absorption_batch(const double* wavelengths, int n_in, const double* nhis,
                                           const double* z_dlas, int S, int num_lines, int broadening, double* out) {
+  return voigt_batch_impl(wavelengths, n_in, nhis, z_dlas, S, num_lines, broadening, 0, out);
+}
+
+extern "C" int dla_voigt_lls_absorption_batch(const double* wavelengths, int n_in, const double* nhis,
+                                              const double* z_llss, int S, int num_lines, int broadening, double* out) {
+  return voigt_batch_impl(wavelengths, n_in, nhis, z_llss, S, num_lines, broadening, 1, out);
+}
+
+extern "C" int dla_spectrum_set_lls_break(dla_spectrum* spec, int on) {
+  DLA_REQUIRE(spec, "null spectrum");
+  spec->lls_break = on ? 1 : 0;
+  return 0;
+}
+
+static int voigt_batch_impl(const double* wavelengths, int n_in, const double* nhis, const double* z_dlas, int S,
+                            int num_lines, int broadening, int lls_break, double* out) {
   DLA_CHECK_READY();
   Runtime& rt = runtime();
   DLA_REQUIRE(wavelengths && nhis && z_dlas && out, "null pointer argument");
@@ -326,6 +347,7 @@ extern "C" int dla_voigt_absorption_batch(const double* wavelengths, int n_in, c
   sp.n_abs = n_in;
   sp.n = n_out;
   sp.broadening = broadening ? 1 : 0;
+  sp.lls_break = lls_break;
   sp.ld = n_out;
   DLA_CUDA(sp.wl_abs.alloc(n_in));
   DLA_CUDA(sp.wl_abs.upload(wavelengths, n_in, rt.stream));

@@ -56,6 +56,7 @@ struct AbsorptionGrid {
   int num_samples;     // rows to produce for this spectrum
   const double* z;     // num_samples absorber redshifts
   const double* nhi;   // num_samples column densities
+  int lls_break;       // add the Lyman-limit break optical depth to the exponent (voigt_lls.py:254-284)
   int pair_offset;     // 0, or S when samples i and i + S share their redshift (the reference's DLA and subDLA
                        // samples use the same offset_samples, set_lls_parameters.m:22 / subdla_samples.py:87):
                        // only the first S samples are launched, each warp evaluates the line sums once
@@ -121,6 +122,15 @@ __device__ __forceinline__ double line_sum_at(double lam, const double* mult, in
   return total;
 }
 
+// Lyman-limit break of an absorber at redshift z (voigt_lls.py:254-284):
+//   tau = nhi / 10^17.2 * (lambda_rest / 911.7641)^3  for lambda_rest <= 911.7641 A, else 0;  returned per unit
+//   (nhi / 10^17.2), i.e. the cube alone, so that paired samples share it
+constexpr double LLS_LIMIT_A = 911.7641;
+__device__ __forceinline__ double lls_break_cube(double lam, double one_plus_z) {
+  const double rest = __ddiv_rn(lam, one_plus_z);
+  return rest > LLS_LIMIT_A ? 0.0 : pow(__ddiv_rn(rest, LLS_LIMIT_A), 3.0);
+}
+
 constexpr int VG_WARPS = 8;  // samples per CTA
 
 // grid = (ceil(max_samples / 8), num_spectra), block = 256, static smem only
@@ -141,6 +151,10 @@ voigt_profile_kernel(const AbsorptionGrid* __restrict__ grids, int num_lines, in
   const double zd = g.z[sample];
   const double nhi = g.nhi[sample];
   const double nhi2 = paired ? g.nhi[sample + g.pair_offset] : 0.0;
+  const bool lls = g.lls_break != 0;
+  const double opz = __dadd_rn(1.0, zd);
+  const double lls_scale = lls ? __ddiv_rn(nhi, pow(10.0, 17.2)) : 0.0;    // np.float64(nhi) / 10**17.2
+  const double lls_scale2 = lls ? __ddiv_rn(nhi2, pow(10.0, 17.2)) : 0.0;
   // multipliers = c / (transition_wavelengths * (1 + z_dla)) / 1e8   (voigt.py:296)
   if (lane < (NL > 0 ? NL : num_lines))
     mult[lane] = __ddiv_rn(__ddiv_rn(LYMAN_C_CGS, __dmul_rn(c_tw_cm[lane], __dadd_rn(1.0, zd))), 1e8);
@@ -151,11 +165,13 @@ voigt_profile_kernel(const AbsorptionGrid* __restrict__ grids, int num_lines, in
   if (!broadening) {
     for (int p0 = 0; p0 < g.n_in; p0 += 32) {
       const int p = p0 + lane;
-      const double total = line_sum_at<NL>(g.wl[min(p, g.n_in - 1)], mult, num_lines);
+      const double lam = g.wl[min(p, g.n_in - 1)];
+      const double total = line_sum_at<NL>(lam, mult, num_lines);
+      const double cube = lls ? lls_break_cube(lam, opz) : 0.0;
       const int q = p < g.n_in ? g.qmap[p] : -1;
       if (q >= 0) {
-        out[q] = profile_exp(nhi * total);
-        if (paired) out2[q] = profile_exp(nhi2 * total);
+        out[q] = profile_exp(__dsub_rn(__dmul_rn(nhi, total), __dmul_rn(lls_scale, cube)));
+        if (paired) out2[q] = profile_exp(__dsub_rn(__dmul_rn(nhi2, total), __dmul_rn(lls_scale2, cube)));
       }
     }
     return;
@@ -168,12 +184,14 @@ voigt_profile_kernel(const AbsorptionGrid* __restrict__ grids, int num_lines, in
   for (int j = 0; j <= nchunks; ++j) {
     if (j < nchunks) {
       const int p = (j << 5) + lane;
-      const double total = line_sum_at<NL>(g.wl[min(p, g.n_in - 1)], mult, num_lines);  // tail lanes: unused copies
-      const double rawv = profile_exp(nhi * total);
+      const double lam = g.wl[min(p, g.n_in - 1)];                     // tail lanes: unused copies
+      const double total = line_sum_at<NL>(lam, mult, num_lines);
+      const double cube = lls ? lls_break_cube(lam, opz) : 0.0;        // warp-uniform branch
+      const double rawv = profile_exp(__dsub_rn(__dmul_rn(nhi, total), __dmul_rn(lls_scale, cube)));
       ring[((j & 1) << 5) + lane] = rawv;
       if ((j & 1) == 0) ring[64 + lane] = rawv;
       if (paired) {
-        const double rawv2 = profile_exp(nhi2 * total);
+        const double rawv2 = profile_exp(__dsub_rn(__dmul_rn(nhi2, total), __dmul_rn(lls_scale2, cube)));
         ring2[((j & 1) << 5) + lane] = rawv2;
         if ((j & 1) == 0) ring2[64 + lane] = rawv2;
       }

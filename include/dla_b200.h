@@ -52,6 +52,11 @@ int dla_voigt_absorption(const double* wavelengths, int n_in, double nhi, double
 int dla_voigt_absorption_batch(const double* wavelengths, int n_in, const double* nhis,
                                const double* z_dlas, int S, int num_lines, int broadening,
                                double* out);
+/* voigt_lls.voigt_absorption (voigt_lls.py:287-363): the same profile with the Lyman-limit break optical
+ * depth tau = nhi / 10^17.2 (lambda_rest / 911.7641)^3 (lambda_rest <= 911.7641 A) added to the exponent */
+int dla_voigt_lls_absorption_batch(const double* wavelengths, int n_in, const double* nhis,
+                                   const double* z_llss, int S, int num_lines, int broadening,
+                                   double* out);
 /* Re w(x + i y) of the profile kernel, exposed for accuracy tests (0 <= y <= 1e-3) */
 int dla_faddeeva_re(const double* x, const double* y, int n, double* out);
 
@@ -99,6 +104,9 @@ int dla_spectrum_create_prepared(const double* y, const double* v, const double*
                                  const double* wl_abs, int n_abs, const uint8_t* keep, int n_u,
                                  int broadening, dla_spectrum** out);
 int dla_spectrum_destroy(dla_spectrum* spec);
+/* absorbers of this spectrum use the Lyman-limit-system profile of voigt_lls.py in every later call
+ * (the extension pattern of examples/gp_find_lls.py:159-224: a DLAGP subclass overriding this_dla_gp) */
+int dla_spectrum_set_lls_break(dla_spectrum* spec, int on);
 /* sizes: n_raw, n_u (in range), n (in range & unmasked) */
 int dla_spectrum_sizes(const dla_spectrum* spec, int* n_raw, int* n_u, int* n);
 /* copy-back of the attributes NullGP holds after set_data (any pointer may be NULL):

@@ -226,7 +226,56 @@ def golden_mcmc():
     print("mcmc_golden.npz written;", int(np.isfinite(post).sum()), "of 40 thetas inside the prior")
 
 
+def golden_lls():
+    """voigt_lls.voigt_absorption and a DLAGP whose this_dla_gp uses it (the pattern of examples/gp_find_lls.py:159-224)."""
+    from gpy_dla_detection import voigt_lls as rl
+
+    loglam = 3.5523 + 1e-4 * np.arange(4650)
+    wl_all = 10.0**loglam
+    z_qso = 3.6
+    sel = (wl_all / (1 + z_qso) >= 850.0) & (wl_all / (1 + z_qso) <= 1215.75)
+    grid = wl_all[sel]  # reaches bluewards of the absorbers' Lyman limit
+    cases = [(3.3, 17.5, 3, True), (3.5, 19.0, 4, True), (3.1, 20.6, 5, False), (3.55, 18.2, 31, True)]
+    out = {"wavelengths": grid, "cases": np.array(cases, dtype=np.float64)}
+    for i, (zl, ln, nl, br) in enumerate(cases):
+        out["profile_%d" % i] = rl.voigt_absorption(grid, 10.0**ln, zl, num_lines=int(nl), broadening=bool(br))
+        out["tau_%d" % i] = rl.tau_LLS_break(grid, 10.0**ln, zl)
+
+    class RLLSGP(RDLAGP):
+        def this_dla_gp(self, z_dlas, nhis):
+            k_dlas = len(z_dlas)
+            mask_ind = ~self.pixel_mask[self.ind_unmasked]
+            absorption = rl.voigt_absorption(self.padded_wavelengths, z_lls=z_dlas[0], nhi=nhis[0],
+                                             num_lines=self.params.num_lines)
+            for j in range(1, k_dlas):
+                absorption = absorption * rl.voigt_absorption(self.padded_wavelengths, z_lls=z_dlas[j], nhi=nhis[j],
+                                                              num_lines=self.params.num_lines)
+            absorption = absorption[mask_ind]
+            return self.this_mu * absorption, self.this_M * absorption[:, None], self.this_omega2 * absorption**2
+
+    S, z_q, seed = 128, 4.2, 17
+    rp = RParameters(num_dla_samples=S, num_lines=4)
+    p = Parameters(num_dla_samples=S, num_lines=4)
+    model = synthetic.make_learned_model(0)
+    prior = synthetic.SyntheticPrior(p)
+    dla = synthetic.make_dla_sample_arrays(p)
+    wl, fl, nv, pm = synthetic.make_spectrum(model, z_q, seed=seed)
+    margs = (model["rest_wavelengths"], model["mu"], model["M"], model["log_omega"], model["log_c_0"],
+             model["log_tau_0"], model["log_beta"])
+    gp = RLLSGP(rp, prior, ref_loader.RefDLASamples(rp, dla), *margs)
+    gp.set_data(rp.emitted_wavelengths(wl, z_q), fl, nv, pm, z_q, build_model=True)
+    np.random.seed(0)
+    ev = gp.log_model_evidences(3)
+    out.update(S=S, z_qso=z_q, seed=seed, log_evidences=ev, sample_log_likelihoods=gp.sample_log_likelihoods,
+               base_sample_inds=gp.base_sample_inds)
+    np.savez_compressed(os.path.join(HERE, "lls_golden.npz"), **out)
+    print("lls_golden.npz written", ev)
+
+
 if __name__ == "__main__":
+    if "--only-lls" in sys.argv:
+        golden_lls()
+        sys.exit(0)
     if "--only-mcmc" in sys.argv:
         golden_mcmc()
         sys.exit(0)
@@ -240,5 +289,6 @@ if __name__ == "__main__":
     golden_spectra()
     golden_zqso()
     golden_mcmc()
+    golden_lls()
     if "--no-full" not in sys.argv:
         golden_full()
