@@ -25,7 +25,9 @@ def test_voigt_lls_golden(gpu):
         # redwards of the limit the break vanishes: identical to the plain Voigt profile there
         plain = voigt.voigt_absorption(wl, 10.0**ln, zl, num_lines=int(nl), broadening=bool(br))
         red = (wl[: got.shape[0]] / (1 + zl)) > voigt_lls.lambda_Lyman_limit + 2.0
-        assert np.array_equal(got[red], plain[red]) and not np.array_equal(got, plain)
+        assert np.array_equal(got[red], plain[red])
+        if np.any(g["tau_%d" % i] > 0):  # the grid reaches bluewards of this absorber's Lyman limit
+            assert not np.array_equal(got, plain)
 
 
 def test_lls_gp_evidences_golden(gpu):
