@@ -17,19 +17,20 @@
 // a dependent chain of a dozen scalar operations costs a warp more time than its 60 DMMAs - measured:
 // the overlapped version of this kernel ran at 22 TFLOP/s, 30 with the producer arithmetic removed.
 // So scalar and tensor work are SEPARATED IN TIME instead of overlapped:
-//   * one CTA of 16 warps per SM owns 64 samples and walks the pixels in 32-pixel panels;
-//   * phase A (all warps, no DMMA in flight): every thread turns 4 profile-cache elements (product of
+//   * a CTA of 8 warps owns 32 samples and walks the pixels in 16-pixel panels, phase A | barrier |
+//     phase B | barrier; two CTAs share an SM, so one CTA's scalar phase runs under the other's DMMAs;
+//   * phase A (all warps of the CTA, none of them issuing DMMAs): every thread turns 2 profile-cache elements (product of
 //     up to 8 absorber factors, dla_gp.py:370-386, loaded during the previous phase B) into the W / G
 //     operand tiles - MUFU-seeded Newton reciprocal, integer-renormalised running product for
 //     sum log d (one log per lane per tile); uncontended, the whole phase is a few hundred cycles;
 //   * phase B (all warps, nothing but LDS + DMMA): warp (rq, cq) owns 16 samples x 7 or 8 of the 30
-//     column blocks, sized [8,7,8,7] / [7,8,7,8] by row quarter so that the four warps of every SM
-//     sub-partition issue 120 DMMAs per 4 pixels: no padding block, four balanced pipes; the loads
+//     column blocks, sized [8,7,8,7] / [7,8,7,8] by row half so that the two warps a CTA has on every SM
+//     sub-partition issue 30 DMMAs per 4 pixels: no padding block, four balanced pipes; the loads
 //     of the next panel's profile rows are in flight underneath;
 //   * the Gram basis [P | M] of the spectrum (n x 240, precomputed once by gram_basis_kernel,
 //     L2-resident) streams through a 2-deep shared-memory ring by TMA bulk copies
 //     (cp.async.bulk + mbarrier complete_tx), requested a full panel ahead;
-//   * the bordered 21 x 21 Cholesky (factor, z = L^-1 c, log-det) of the 64 samples is a third,
+//   * the bordered 21 x 21 Cholesky (factor, z = L^-1 c, log-det) of the 32 samples is a third,
 //     purely scalar phase: 8 threads per sample, straight out of the accumulator fragments.
 // HBM sees only the profile rows (read) and one double per sample (written).
 #pragma once
@@ -39,22 +40,25 @@ namespace dla {
 
 constexpr int LK_K = 20;                         // rank of the learned covariance (Parameters.k)
 constexpr int LK_PAIRS = LK_K * (LK_K + 1) / 2;  // 210 lower-triangle pairs
-constexpr int LK_TS = 64;                        // samples per CTA tile
-constexpr int LK_KC = 32;                        // pixels per panel
-constexpr int LK_WSTRIDE = LK_KC + 4;            // row stride of the W/G tiles (36 == 4 mod 16: conflict-free A loads)
+constexpr int LK_TS = 32;                        // samples per CTA tile
+constexpr int LK_KC = 16;                        // pixels per panel
+constexpr int LK_WSTRIDE = LK_KC + 4;            // row stride of the W/G tiles (== 4 mod 16: conflict-free A loads)
 constexpr int LK_NBLK_PAIR = 27;                 // ceil(210 / 8) column blocks of the Gram part
 constexpr int LK_NBLK = 30;                      // + 3 column blocks (24 >= 20) of the projection part
 constexpr int LK_NCOLS = LK_NBLK * 8;            // 240
 constexpr int LK_PSTRIDE = LK_NCOLS + 4;         // basis row stride (244 == 4 mod 16: conflict-free B loads)
 constexpr int LK_PROJ_COL0 = LK_NBLK_PAIR * 8;   // 216: first projection column
-constexpr int LK_WARPS = 16;
+constexpr int LK_WARPS = 8;
 constexpr int LK_THREADS = LK_WARPS * 32;        // 512
 constexpr int LK_PSTAGES = 2;                    // basis-panel ring (TMA)
+constexpr int LK_CTAS_PER_SM = 2;               // (64 x 32 tiles, 16 warps, 1 CTA/SM measured 3 % slower)
 constexpr int LK_EP_STRIDE = LK_TS + 1;          // epilogue smem: [col][sample], stride 65
 constexpr int LK_MAX_ROWS = 8;                   // max absorbers multiplied per sample (max_dlas <= 8)
 constexpr int LK_MB = 2;                         // DMMA row blocks per warp (16 samples)
 constexpr int LK_NB_MAX = 8;                     // DMMA column blocks per warp (7 or 8)
-constexpr int LK_EPT = LK_TS * LK_KC / LK_THREADS;  // W/G elements per thread per panel (4)
+constexpr int LK_EPT = LK_TS * LK_KC / LK_THREADS;  // W/G elements per thread per panel
+constexpr int LK_PSTEP = LK_THREADS / LK_KC;        // sample stride between the elements of a thread
+static_assert(LK_KC <= 32 && LK_THREADS % LK_KC == 0 && LK_TS * 8 == LK_THREADS && LK_WARPS == LK_TS / 4, "tile shape");
 constexpr double LK_LOG_2PI = 1.83787706640934534;  // null_gp.py:325
 constexpr double LK_LN2 = 0.693147180559945309417232121458;
 
@@ -173,27 +177,27 @@ __device__ __forceinline__ double fast_rcp(double d) {
   return (d > 1e-290 && d < 1e290) ? r : r0;
 }
 
-// ---- shared memory plan (one CTA per SM) ------------------------------------------------------------
-//   basis ring : 2 x [32][244]                                             124 928 B
-//   W | G      : [64][36] each                                              36 864 B
-//   RAW        : profile-row panels of factor 0 and factor 1 [64][32] each, pixel scalars [4][32]
-//                (filled by cp.async during phase B, read in phase A)          33 792 B
-//   E          : epilogue matrix [240][65], overlays the above             124 800 B
-//   AUX        : per-sample sums [64][2], profile rows [8][64], 2 mbarriers
-constexpr int LK_PANEL_DOUBLES = LK_KC * LK_PSTRIDE;               // 7808
-constexpr int LK_WG_DOUBLES = LK_TS * LK_WSTRIDE;                  // 2304
-constexpr uint32_t LK_PANEL_BYTES = LK_PANEL_DOUBLES * sizeof(double);  // 62 464
-constexpr int LK_RAW_DOUBLES = 2 * LK_TS * LK_KC + 4 * LK_KC;       // 4224
-constexpr int LK_RING_DOUBLES = LK_PSTAGES * LK_PANEL_DOUBLES + 2 * LK_WG_DOUBLES + LK_RAW_DOUBLES;  // 24 448
-constexpr int LK_EP_DOUBLES = LK_NCOLS * LK_EP_STRIDE;             // 15 600
+// ---- shared memory plan (two CTAs per SM) -----------------------------------------------------------
+//   basis ring : 2 x [16][244]                                              62 464 B
+//   W | G      : [32][20] each                                              10 240 B
+//   RAW        : profile-row panels of factor 0 and factor 1 [32][16] each, pixel scalars [4][16]
+//                (filled by cp.async during phase B, read in phase A)           8 704 B
+//   E          : epilogue matrix [240][33], overlays the above              63 360 B
+//   AUX        : per-sample sums [32][2], profile rows [8][32], 2 mbarriers
+constexpr int LK_PANEL_DOUBLES = LK_KC * LK_PSTRIDE;               // 3904
+constexpr int LK_WG_DOUBLES = LK_TS * LK_WSTRIDE;                  // 640
+constexpr uint32_t LK_PANEL_BYTES = LK_PANEL_DOUBLES * sizeof(double);  // 31 232
+constexpr int LK_RAW_DOUBLES = 2 * LK_TS * LK_KC + 4 * LK_KC;       // 1088
+constexpr int LK_RING_DOUBLES = LK_PSTAGES * LK_PANEL_DOUBLES + 2 * LK_WG_DOUBLES + LK_RAW_DOUBLES;  // 10 176
+constexpr int LK_EP_DOUBLES = LK_NCOLS * LK_EP_STRIDE;             // 7920
 constexpr int LK_MAIN_DOUBLES = LK_RING_DOUBLES > LK_EP_DOUBLES ? LK_RING_DOUBLES : LK_EP_DOUBLES;
 constexpr size_t LK_AUX_BYTES = LK_TS * 2 * sizeof(double) + LK_MAX_ROWS * LK_TS * sizeof(int32_t) +
                                 LK_PSTAGES * sizeof(uint64_t);
 constexpr size_t LK_SMEM_BYTES = (size_t)LK_MAIN_DOUBLES * sizeof(double) + LK_AUX_BYTES;
 static_assert(LK_PANEL_BYTES % 128 == 0, "TMA alignment");
 
-// grid = (ceil(max num_samples / 64), num_spectra), block = 512, dynamic smem = LK_SMEM_BYTES
-__global__ void __launch_bounds__(LK_THREADS, 1)
+// grid = (ceil(max num_samples / 32), num_spectra), block = 256, dynamic smem = LK_SMEM_BYTES
+__global__ void __launch_bounds__(LK_THREADS, LK_CTAS_PER_SM)
 sample_likelihood_kernel(const LikelihoodSpectrum* __restrict__ specs) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   const LikelihoodSpectrum sp = specs[blockIdx.y];
@@ -245,13 +249,14 @@ sample_likelihood_kernel(const LikelihoodSpectrum* __restrict__ specs) {
   }
   __syncthreads();
 
-  // ---- producer role: warp w -> samples w, w+16, w+32, w+48 ; lane -> pixel of the panel -----------
-  // (a warp stores 32 consecutive doubles of one W/G row: conflict-free; and reads 256 contiguous
+  // ---- producer role: thread -> pixel pl of the panel and samples ps0 + e * LK_PSTEP ----------------
+  // (consecutive threads store consecutive doubles of one W/G row: conflict-free; and read contiguous
   //  bytes of a profile row)
+  const int pl = tid % LK_KC, ps0 = tid / LK_KC;
   const bool two_rows = num_rows > 1;
   unsigned live = 0;
 #pragma unroll
-  for (int e = 0; e < LK_EPT; ++e) live |= (tile_s0 + warp + LK_WARPS * e < sp.num_samples ? 1u : 0u) << e;
+  for (int e = 0; e < LK_EPT; ++e) live |= (tile_s0 + ps0 + LK_PSTEP * e < sp.num_samples ? 1u : 0u) << e;
   double q_acc[LK_EPT], dprod[LK_EPT];
   int esum[LK_EPT];
 #pragma unroll
@@ -274,12 +279,12 @@ sample_likelihood_kernel(const LikelihoodSpectrum* __restrict__ specs) {
   // stage the inputs of `panel` in shared memory with cp.async: issued at the start of phase B, so the
   // copies fly underneath the DMMAs and no register is held for them (a register prefetch of 4 elements
   // x 2 factors spilled, and the spill store waited for the load)
-  // `nthreads` threads with rank `r` (all 512 in the prologue; in the main loop the 8 warps that own
+  // `nthreads` threads with rank `r` (the whole CTA in the prologue; in the main loop the warps that own
   // only 7 column blocks, i.e. the ones with 1/8 less DMMA work)
   auto stage_panel = [&](int panel, int r, int nthreads) {
     const int p0 = panel * LK_KC;
-    for (int idx = r; idx < LK_TS * LK_KC / 2; idx += nthreads) {  // 16-byte chunks: 16 per sample row
-      const int s = idx >> 4, j = (idx & 15) * 2;
+    for (int idx = r; idx < LK_TS * LK_KC / 2; idx += nthreads) {  // 16-byte chunks: KC / 2 per sample row
+      const int s = idx / (LK_KC / 2), j = (idx % (LK_KC / 2)) * 2;
       const int p = p0 + j;
       const int ok = p < sp.ld ? 16 : 0;  // rows are padded to ld (multiple of 4): zero-fill beyond
       const size_t off = (size_t)min(p, sp.ld - 2);
@@ -287,7 +292,7 @@ sample_likelihood_kernel(const LikelihoodSpectrum* __restrict__ specs) {
       if (two_rows) cp_async16_zfill(s_raw1 + s * LK_KC + j, sp.cache + (size_t)s_rows[LK_TS + s] * sp.ld + off, ok);
     }
     if (r < 4 * LK_KC) {
-      const int arr = r >> 5, j = r & 31;
+      const int arr = r / LK_KC, j = r % LK_KC;
       const double* src = arr == 0 ? sp.y : arr == 1 ? sp.mu : arr == 2 ? sp.omega2 : sp.v;
       cp_async8(s_pix + arr * LK_KC + j, src + min(p0 + j, n - 1));
     }
@@ -299,29 +304,29 @@ sample_likelihood_kernel(const LikelihoodSpectrum* __restrict__ specs) {
   // thread (a = 0, y = mu = omega2 = 0, v = 1  =>  w = g = 0, d = 1); samples beyond num_samples (last
   // tile of a spectrum) compute on row 0 and are simply never written out - no per-element selects.
   auto produce = [&](int panel) {
-    const int p = panel * LK_KC + lane;
+    const int p = panel * LK_KC + pl;
     const bool pv = p < n;
-    const double yp = pv ? s_pix[lane] : 0.0, mup = pv ? s_pix[LK_KC + lane] : 0.0;
-    const double omp = pv ? s_pix[2 * LK_KC + lane] : 0.0, vp = pv ? s_pix[3 * LK_KC + lane] : 1.0;
+    const double yp = pv ? s_pix[pl] : 0.0, mup = pv ? s_pix[LK_KC + pl] : 0.0;
+    const double omp = pv ? s_pix[2 * LK_KC + pl] : 0.0, vp = pv ? s_pix[3 * LK_KC + pl] : 1.0;
     double a[LK_EPT];
 #pragma unroll
-    for (int e = 0; e < LK_EPT; ++e) a[e] = s_raw0[(warp + LK_WARPS * e) * LK_KC + lane];
+    for (int e = 0; e < LK_EPT; ++e) a[e] = s_raw0[(ps0 + LK_PSTEP * e) * LK_KC + pl];
     // absorption = product of the factors' profiles, left to right (dla_gp.py:370-386)
     if (two_rows) {
 #pragma unroll
-      for (int e = 0; e < LK_EPT; ++e) a[e] = a[e] * s_raw1[(warp + LK_WARPS * e) * LK_KC + lane];
+      for (int e = 0; e < LK_EPT; ++e) a[e] = a[e] * s_raw1[(ps0 + LK_PSTEP * e) * LK_KC + pl];
     }
     if (num_rows > 2) {  // rare: dla_sample_log_likelihoods with more than two absorbers per sample
       const int pc = min(p, n - 1);
 #pragma unroll
       for (int e = 0; e < LK_EPT; ++e)
         for (int r = 2; r < num_rows; ++r)
-          a[e] = a[e] * sp.cache[(size_t)s_rows[r * LK_TS + warp + LK_WARPS * e] * sp.ld + pc];
+          a[e] = a[e] * sp.cache[(size_t)s_rows[r * LK_TS + ps0 + LK_PSTEP * e] * sp.ld + pc];
     }
     if (sp.prod_out && pv) {
 #pragma unroll
       for (int e = 0; e < LK_EPT; ++e)
-        if ((live >> e) & 1u) sp.prod_out[(size_t)(tile_s0 + warp + LK_WARPS * e) * sp.ld + p] = a[e];
+        if ((live >> e) & 1u) sp.prod_out[(size_t)(tile_s0 + ps0 + LK_PSTEP * e) * sp.ld + p] = a[e];
     }
     // the four elements advance in lock step (one loop per operation): four independent dependency
     // chains in flight instead of one after the other
@@ -350,9 +355,9 @@ sample_likelihood_kernel(const LikelihoodSpectrum* __restrict__ specs) {
     for (int e = 0; e < LK_EPT; ++e) t[e] = res[e] * inv[e];
 #pragma unroll
     for (int e = 0; e < LK_EPT; ++e) {
-      const int s = warp + LK_WARPS * e;
-      s_W[s * LK_WSTRIDE + lane] = a2[e] * inv[e];
-      s_G[s * LK_WSTRIDE + lane] = a[e] * t[e];
+      const int s = ps0 + LK_PSTEP * e;
+      s_W[s * LK_WSTRIDE + pl] = a2[e] * inv[e];
+      s_G[s * LK_WSTRIDE + pl] = a[e] * t[e];
     }
 #pragma unroll
     for (int e = 0; e < LK_EPT; ++e) q_acc[e] = fma(res[e], t[e], q_acc[e]);
@@ -373,7 +378,7 @@ sample_likelihood_kernel(const LikelihoodSpectrum* __restrict__ specs) {
   const int first = !odd ? (cq == 0 ? 0 : cq == 1 ? 8 : cq == 2 ? 15 : 23) : (cq == 0 ? 0 : cq == 1 ? 7 : cq == 2 ? 15 : 22);
   const bool has_eighth = ((cq + (odd ? 1 : 0)) & 1) == 0;
   const bool g4 = first + 4 >= LK_NBLK_PAIR, g5 = first + 5 >= LK_NBLK_PAIR;
-  const int stage_rank = (rq * 2 + (cq >> 1)) * 32 + lane;  // rank among the 256 threads of the 7-block warps
+  const int stage_rank = (rq * 2 + (cq >> 1)) * 32 + lane;  // rank among the threads of the 7-block warps
   double acc[LK_MB][LK_NB_MAX][2];
 #pragma unroll
   for (int m = 0; m < LK_MB; ++m)
@@ -446,20 +451,20 @@ sample_likelihood_kernel(const LikelihoodSpectrum* __restrict__ specs) {
     __syncthreads();                                              // W/G and the basis stage are free, inputs staged
   }
 
-  // per-sample scalar sums: reduce over the 32 pixel lanes
+  // per-sample scalar sums: reduce over the pixel lanes of the panel
   renorm();
 #pragma unroll
   for (int e = 0; e < LK_EPT; ++e) {
     double q = q_acc[e];
     double l = fma((double)esum[e], LK_LN2, log(dprod[e]));
 #pragma unroll
-    for (int off = 16; off > 0; off >>= 1) {
+    for (int off = (LK_KC < 32 ? LK_KC : 32) / 2; off > 0; off >>= 1) {
       q += __shfl_xor_sync(0xffffffffu, q, off);
       l += __shfl_xor_sync(0xffffffffu, l, off);
     }
-    if (lane == 0) {
-      s_sums[(warp + LK_WARPS * e) * 2] = q;
-      s_sums[(warp + LK_WARPS * e) * 2 + 1] = l;
+    if (pl == 0) {
+      s_sums[(ps0 + LK_PSTEP * e) * 2] = q;
+      s_sums[(ps0 + LK_PSTEP * e) * 2 + 1] = l;
     }
   }
 
@@ -490,7 +495,7 @@ sample_likelihood_kernel(const LikelihoodSpectrum* __restrict__ specs) {
   // dot product is two independent FMA chains.  (The first version walked the matrix in shared memory with
   // two loads per FMA and took 13 % of the kernel with the tensor pipe idle.)
   {
-    const int s = tid >> 3;          // sample of this thread group (64 samples x 8 threads = 512)
+    const int s = tid >> 3;          // sample of this thread group (8 threads per sample)
     const int t = tid & 7;
     const int gbase = lane & ~7;
     const double* Es = E + s;
