@@ -350,7 +350,12 @@ sample_likelihood_kernel(const LikelihoodSpectrum* __restrict__ specs) {
 #pragma unroll
     for (int e = 0; e < LK_EPT; ++e) inv[e] = fma(inv[e], er[e], inv[e]);
 #pragma unroll
-    for (int e = 0; e < LK_EPT; ++e) inv[e] = (d[e] > 1e-290 && d[e] < 1e290) ? inv[e] : r0[e];  // see fast_rcp
+    for (int e = 0; e < LK_EPT; ++e) {
+      // see fast_rcp: outside roughly [1e-290, 1e290] (and for 0, inf, NaN, negative d) keep the seed.  The test
+      // is on the exponent field with integer instructions - a DSETP would queue on the FP64 pipe like a DFMA
+      const unsigned hi = (unsigned)__double2hiint(d[e]);
+      inv[e] = (hi - 0x03d00000u < 0x7c300000u - 0x03d00000u) ? inv[e] : r0[e];
+    }
 #pragma unroll
     for (int e = 0; e < LK_EPT; ++e) t[e] = res[e] * inv[e];
 #pragma unroll
