@@ -379,7 +379,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--spectra", type=int, default=1000, help="spectra per step per GPU")
-    ap.add_argument("--batch", type=int, default=64, help="spectra resident per device batch")
+    ap.add_argument("--batch", type=int, default=128, help="spectra resident per device batch")
     ap.add_argument("--skip-cpu", action="store_true", help="skip the cpu_baseline leg")
     args = ap.parse_args()
     if args.impl == "reference":
