@@ -11,30 +11,40 @@
 //     [B_s - I | c_s] = [W | G] x [P | M] ,   P[p,(i,j)] = m_pi m_pj  (i >= j, 210 pairs)
 // on the FP64 tensor path (DMMA m8n8k4).
 //
-// The design follows from one measured fact: on B200 the DMMA path and the scalar FP64 pipe are
-// the same 64 FMA lanes/SM/clk (37 TFLOP/s either way; mixed stream 35).  A scalar FP64 instruction
-// issued while DMMAs saturate that pipe waits for a DMMA slot (16 cycles each, several queued), so
-// a dependent chain of a dozen scalar operations costs a warp more time than its 60 DMMAs - measured:
-// the overlapped version of this kernel ran at 22 TFLOP/s, 30 with the producer arithmetic removed.
-// So scalar and tensor work are SEPARATED IN TIME instead of overlapped:
-//   * a CTA of 8 warps owns 32 samples and walks the pixels in 16-pixel panels, phase A | barrier |
-//     phase B | barrier; two CTAs share an SM, so one CTA's scalar phase runs under the other's DMMAs;
-//   * phase A (all warps of the CTA, none of them issuing DMMAs): every thread turns 2 profile-cache elements (product of
-//     up to 8 absorber factors, dla_gp.py:370-386, loaded during the previous phase B) into the W / G
-//     operand tiles - MUFU-seeded Newton reciprocal, integer-renormalised running product for
-//     sum log d (one log per lane per tile); uncontended, the whole phase is a few hundred cycles;
-//   * phase B (all warps, nothing but LDS + DMMA): warp (rq, cq) owns 16 samples x 7 or 8 of the 30
-//     column blocks, sized [8,7,8,7] / [7,8,7,8] by row half so that the two warps a CTA has on every SM
-//     sub-partition issue 30 DMMAs per 4 pixels: no padding block, four balanced pipes; the loads
-//     of the next panel's profile rows are in flight underneath;
+// The design follows from measurements on B200 (tools/fp64_peaks.cu, fp64_contention_probe.cu,
+// fp64_interleave_probe.cu, dmma_feed_probe.cu):
+//   * the DMMA path and the scalar FP64 pipe are the same 64 FMA lanes/SM/clk (37 TFLOP/s either way);
+//   * a warp issuing scalar FP64 operations is STARVED while two or more other warps of its SM sub-partition
+//     issue back-to-back DMMAs (a dependent DFMA then takes > 20 000 cycles), so producer warps, or a producer
+//     phase of one CTA running under the DMMA phase of another, do not work (18.5 and 26.9 TFLOP/s);
+//   * when every warp carries the same mix - two DMMAs, one scalar operation - the pipe stays 91 % busy;
+//   * a DMMA loop fed from shared memory in this kernel's layout, with a CTA barrier per 16-pixel panel,
+//     runs at 95-97 % of the peak, and every non-FP64 instruction a warp executes per panel (address
+//     arithmetic, staging, selects) costs throughput: the warps of a sub-partition take turns on one pipe and
+//     their own instruction streams are the think time of that queue.
+// So every warp runs ONE instruction stream per panel: the DMMAs of panel p with the scalar arithmetic that
+// produces the W / G operand tiles of panel p + 1 threaded through them, and as little else as possible:
+//   * a CTA of 8 warps owns 32 samples and walks the pixels in 16-pixel panels, one barrier per panel, two
+//     panels per loop trip so that all buffer parities are compile-time and every shared-memory address is a
+//     per-thread base plus an immediate; two CTAs share an SM;
+//   * scalar work: every thread turns 2 profile-cache elements (product of up to 8 absorber factors,
+//     dla_gp.py:370-386) into W / G entries - MUFU-seeded reciprocal with one cubic correction,
+//     integer-renormalised running product for sum log d (one log per lane per tile), no validity selects
+//     (the last panel is staged with neutral values beyond n);
+//   * DMMA work: warp (rq, cq) owns 16 samples x 7 or 8 of the 30 column blocks, sized [8,7,8,7] / [7,8,7,8]
+//     by row half so that the two warps a CTA has on every SM sub-partition issue 30 DMMAs per 4 pixels: no
+//     padding block, four balanced pipes;
+//   * the profile rows of panel p + 2 are staged by cp.async (row pointers from a shared-memory table: a
+//     pointer load, an add and the LDGSTS per 16 bytes), issued by the warps that own only 7 blocks;
 //   * the Gram basis [P | M] of the spectrum (n x 240, precomputed once by gram_basis_kernel,
 //     L2-resident) streams through a 2-deep shared-memory ring by TMA bulk copies
 //     (cp.async.bulk + mbarrier complete_tx), requested a full panel ahead;
-//   * the bordered 21 x 21 Cholesky (factor, z = L^-1 c, log-det) of the 32 samples is a third,
+//   * the bordered 21 x 21 Cholesky (factor, z = L^-1 c, log-det) of the 32 samples is a final,
 //     purely scalar phase: 8 threads per sample, straight out of the accumulator fragments.
 // HBM sees only the profile rows (read) and one double per sample (written).
 #pragma once
 #include <stdint.h>
+#include <type_traits>
 
 namespace dla {
 
@@ -128,6 +138,34 @@ __device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double
       : "d"(a), "d"(b));
 }
 
+// Order-pinned variants for the interleaved main loop: volatile asm statements keep their program order,
+// so the scalar operations stay where they were placed between the DMMAs.
+__device__ __forceinline__ void dmma884_pinned(double& c0, double& c1, double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+               : "+d"(c0), "+d"(c1)
+               : "d"(a), "d"(b));
+}
+__device__ __forceinline__ double fma_pinned(double a, double b, double c) {
+  double r;
+  asm volatile("fma.rn.f64 %0, %1, %2, %3;" : "=d"(r) : "d"(a), "d"(b), "d"(c));
+  return r;
+}
+__device__ __forceinline__ double fnma_pinned(double a, double b, double c) {  // -a b + c
+  double r;
+  asm volatile("{\n.reg .f64 na;\nneg.f64 na, %1;\nfma.rn.f64 %0, na, %2, %3;\n}" : "=d"(r) : "d"(a), "d"(b), "d"(c));
+  return r;
+}
+__device__ __forceinline__ double mul_pinned(double a, double b) {
+  double r;
+  asm volatile("mul.rn.f64 %0, %1, %2;" : "=d"(r) : "d"(a), "d"(b));
+  return r;
+}
+__device__ __forceinline__ double rcp_seed(double d) {  // MUFU.RCP64H: SFU, not the FP64 pipe
+  double r;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(d));
+  return r;
+}
+
 // ---- mbarrier + TMA bulk copy -----------------------------------------------------------------------
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
@@ -156,12 +194,24 @@ __device__ __forceinline__ void cp_async8(void* smem_dst, const void* gmem_src) 
   const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
   asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"(d), "l"(gmem_src) : "memory");
 }
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src) {
+  const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(d), "l"(gmem_src) : "memory");
+}
 __device__ __forceinline__ void cp_async16_zfill(void* smem_dst, const void* gmem_src, int src_bytes) {
   const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(d), "l"(gmem_src), "r"(src_bytes) : "memory");
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;\n" ::: "memory"); }
+
+// factors 2 .. num_rows - 1 of a sample (dla_sample_log_likelihoods with more than two absorbers per sample):
+// rare, kept out of line so that the main loop stays small
+__device__ __noinline__ double times_extra_factors(double a, const double* cache, const int32_t* rows_of_sample,
+                                                   int num_rows, int ld, int p) {
+  for (int r = 2; r < num_rows; ++r) a = a * cache[(size_t)rows_of_sample[r * LK_TS] * ld + p];
+  return a;
+}
 
 // 1/d for the operand tiles: MUFU.RCP64H seed (SFU, not the FP64 pipe) + two Newton steps (4 DFMA),
 // <= 1 ulp from the IEEE quotient.  Branch-free, so the four elements of a thread interleave: outside
@@ -177,22 +227,22 @@ __device__ __forceinline__ double fast_rcp(double d) {
   return (d > 1e-290 && d < 1e290) ? r : r0;
 }
 
-// ---- shared memory plan (two CTAs per SM) -----------------------------------------------------------
-//   basis ring : 2 x [16][244]                                              62 464 B
-//   W | G      : [32][20] each                                              10 240 B
-//   RAW        : profile-row panels of factor 0 and factor 1 [32][16] each, pixel scalars [4][16]
-//                (filled by cp.async during phase B, read in phase A)           8 704 B
-//   E          : epilogue matrix [240][33], overlays the above              63 360 B
-//   AUX        : per-sample sums [32][2], profile rows [8][32], 2 mbarriers
+// ---- shared memory plan (two CTAs per SM, 102 448 B each) ----------------------------------------------
+//   basis ring : 2 x [16][244]                                                          62 464 B
+//   W | G      : 2 buffers x { W [32][20], G [32][20] } (read by the DMMAs / written for the next panel) 20 480 B
+//   RAW        : 2 buffers x { profile-row panels of factor 0 and factor 1 [32][16] each, y, mu, omega2, v [4][16] }
+//                (read by the scalar slots / filled by cp.async for the panel after)           17 408 B
+//   E          : epilogue matrix [240][33], overlays the above                          63 360 B
+//   AUX        : per-sample sums [32][2], profile row indices [8][32], row pointers [2][32] + 4, 2 mbarriers
 constexpr int LK_PANEL_DOUBLES = LK_KC * LK_PSTRIDE;               // 3904
 constexpr int LK_WG_DOUBLES = LK_TS * LK_WSTRIDE;                  // 640
 constexpr uint32_t LK_PANEL_BYTES = LK_PANEL_DOUBLES * sizeof(double);  // 31 232
 constexpr int LK_RAW_DOUBLES = 2 * LK_TS * LK_KC + 4 * LK_KC;       // 1088
-constexpr int LK_RING_DOUBLES = LK_PSTAGES * LK_PANEL_DOUBLES + 2 * LK_WG_DOUBLES + LK_RAW_DOUBLES;  // 10 176
+constexpr int LK_RING_DOUBLES = LK_PSTAGES * LK_PANEL_DOUBLES + 2 * (2 * LK_WG_DOUBLES + LK_RAW_DOUBLES);  // 12 544
 constexpr int LK_EP_DOUBLES = LK_NCOLS * LK_EP_STRIDE;             // 7920
 constexpr int LK_MAIN_DOUBLES = LK_RING_DOUBLES > LK_EP_DOUBLES ? LK_RING_DOUBLES : LK_EP_DOUBLES;
 constexpr size_t LK_AUX_BYTES = LK_TS * 2 * sizeof(double) + LK_MAX_ROWS * LK_TS * sizeof(int32_t) +
-                                LK_PSTAGES * sizeof(uint64_t);
+                                (2 * LK_TS + 4) * sizeof(void*) + LK_PSTAGES * sizeof(uint64_t);
 constexpr size_t LK_SMEM_BYTES = (size_t)LK_MAIN_DOUBLES * sizeof(double) + LK_AUX_BYTES;
 static_assert(LK_PANEL_BYTES % 128 == 0, "TMA alignment");
 
@@ -206,14 +256,15 @@ sample_likelihood_kernel(const LikelihoodSpectrum* __restrict__ specs) {
   if (sp.alive && *sp.alive == 0) return;
 
   double* s_main = reinterpret_cast<double*>(smem_raw);
-  double* s_W = s_main + LK_PSTAGES * LK_PANEL_DOUBLES;
-  double* s_G = s_W + LK_WG_DOUBLES;
-  double* s_raw0 = s_G + LK_WG_DOUBLES;      // [64][32] factor-0 profile values of the staged panel
-  double* s_raw1 = s_raw0 + LK_TS * LK_KC;   // [64][32] factor-1 profile values
-  double* s_pix = s_raw1 + LK_TS * LK_KC;    // [4][32]  y, mu, omega2, v of the staged panel
-  double* s_sums = s_main + LK_MAIN_DOUBLES;                          // [64][2] : sum r^2/d, sum log d
-  int32_t* s_rows = reinterpret_cast<int32_t*>(s_sums + LK_TS * 2);   // [num_rows][64]
-  uint64_t* s_mbar = reinterpret_cast<uint64_t*>(s_rows + LK_MAX_ROWS * LK_TS);  // basis panel landed [2]
+  double* s_WG = s_main + LK_PSTAGES * LK_PANEL_DOUBLES;  // 2 buffers x { W [32][20], G [32][20] }
+  double* s_RAW = s_WG + 2 * 2 * LK_WG_DOUBLES;           // 2 buffers x { factor-0 rows [32][16], factor-1 rows [32][16],
+                                                          //               y, mu, omega2, v [4][16] } of a staged panel
+  double* s_sums = s_main + LK_MAIN_DOUBLES;                          // [32][2] : sum r^2/d, sum log d
+  int32_t* s_rows = reinterpret_cast<int32_t*>(s_sums + LK_TS * 2);   // [num_rows][32]
+  const double** s_ptr0 = reinterpret_cast<const double**>(s_rows + LK_MAX_ROWS * LK_TS);  // [32] factor-0 row of each sample
+  const double** s_ptr1 = s_ptr0 + LK_TS;                                                    // [32] factor-1 row
+  const double** s_pixptr = s_ptr1 + LK_TS;                                                  // y, mu, omega2, v
+  uint64_t* s_mbar = reinterpret_cast<uint64_t*>(s_pixptr + 4);  // basis panel landed [2]
 
   const int tid = threadIdx.x;
   const int warp = tid >> 5, lane = tid & 31;
@@ -240,7 +291,10 @@ sample_likelihood_kernel(const LikelihoodSpectrum* __restrict__ specs) {
       else row = sp.rows ? sp.rows[(size_t)(r - 1) * sp.row_stride + gs] : sp.row0 + r * sp.row_stride + gs;
     }
     s_rows[r * LK_TS + s] = row;
+    if (r == 0) s_ptr0[s] = sp.base0 + (size_t)row * sp.ld;
+    if (r == 1) s_ptr1[s] = sp.cache + (size_t)row * sp.ld;
   }
+  if (tid < 4) s_pixptr[tid] = tid == 0 ? sp.y : tid == 1 ? sp.mu : tid == 2 ? sp.omega2 : sp.v;
   if (tid == 0) {
 #pragma unroll
     for (int s = 0; s < LK_PSTAGES; ++s) mbar_init(bar_base + 8u * s, 1);
@@ -276,104 +330,120 @@ sample_likelihood_kernel(const LikelihoodSpectrum* __restrict__ specs) {
     }
   };
 
-  // stage the inputs of `panel` in shared memory with cp.async: issued at the start of phase B, so the
-  // copies fly underneath the DMMAs and no register is held for them (a register prefetch of 4 elements
-  // x 2 factors spilled, and the spill store waited for the load)
-  // `nthreads` threads with rank `r` (the whole CTA in the prologue; in the main loop the warps that own
-  // only 7 column blocks, i.e. the ones with 1/8 less DMMA work)
-  auto stage_panel = [&](int panel, int r, int nthreads) {
+  // stage the inputs of `panel` in RAW buffer PAR (= panel & 1) with cp.async: the copies fly underneath the
+  // DMMAs and no register is held for them.  `nthreads` threads with rank `r` (the whole CTA in the
+  // prologue; in the main loop the warps that own only 7 column blocks, i.e. 1/8 less DMMA work).
+  // A thread always copies the same 16-byte column chunk jc of samples r / 8 + k nthreads / 8; the row base
+  // pointers come from a shared-memory table, so a chunk costs a pointer load, an add and the LDGSTS.
+  // Every panel but the last lies inside all rows (p0 + 16 <= n <= ld).  The last one is copied element by
+  // element, and what lies beyond n is written as neutral values (a = 0, y = mu = omega2 = 0, v = 1 =>
+  // w = g = 0, d = 1) so that the arithmetic needs no validity test.
+  auto stage_panel = [&](const int panel, auto par_tag, const int r, const int nthreads) {
+    constexpr int PAR = decltype(par_tag)::value;
+    double* raw0 = s_RAW + PAR * LK_RAW_DOUBLES;
+    double* raw1 = raw0 + LK_TS * LK_KC;
+    double* pix = raw1 + LK_TS * LK_KC;
     const int p0 = panel * LK_KC;
-    for (int idx = r; idx < LK_TS * LK_KC / 2; idx += nthreads) {  // 16-byte chunks: KC / 2 per sample row
-      const int s = idx / (LK_KC / 2), j = (idx % (LK_KC / 2)) * 2;
-      const int p = p0 + j;
-      const int ok = p < sp.ld ? 16 : 0;  // rows are padded to ld (multiple of 4): zero-fill beyond
-      const size_t off = (size_t)min(p, sp.ld - 2);
-      cp_async16_zfill(s_raw0 + s * LK_KC + j, sp.base0 + (size_t)s_rows[s] * sp.ld + off, ok);
-      if (two_rows) cp_async16_zfill(s_raw1 + s * LK_KC + j, sp.cache + (size_t)s_rows[LK_TS + s] * sp.ld + off, ok);
-    }
-    if (r < 4 * LK_KC) {
-      const int arr = r / LK_KC, j = r % LK_KC;
-      const double* src = arr == 0 ? sp.y : arr == 1 ? sp.mu : arr == 2 ? sp.omega2 : sp.v;
-      cp_async8(s_pix + arr * LK_KC + j, src + min(p0 + j, n - 1));
+    const int jc = (r % (LK_KC / 2)) * 2;
+    if (panel + 1 < npanels) {
+      const size_t boff = (size_t)(p0 + jc) * sizeof(double);
+      for (int sidx = r / (LK_KC / 2); sidx < LK_TS; sidx += nthreads / (LK_KC / 2)) {
+        cp_async16(raw0 + sidx * LK_KC + jc, reinterpret_cast<const char*>(s_ptr0[sidx]) + boff);
+        if (two_rows) cp_async16(raw1 + sidx * LK_KC + jc, reinterpret_cast<const char*>(s_ptr1[sidx]) + boff);
+      }
+      if (r < 4 * LK_KC) cp_async8(pix + r, s_pixptr[r / LK_KC] + p0 + r % LK_KC);
+    } else {
+      for (int sidx = r / (LK_KC / 2); sidx < LK_TS; sidx += nthreads / (LK_KC / 2)) {
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          const int p = p0 + jc + h;
+          if (p < n) {
+            cp_async8(raw0 + sidx * LK_KC + jc + h, s_ptr0[sidx] + p);
+            if (two_rows) cp_async8(raw1 + sidx * LK_KC + jc + h, s_ptr1[sidx] + p);
+          } else {
+            raw0[sidx * LK_KC + jc + h] = 0.0;
+            raw1[sidx * LK_KC + jc + h] = 0.0;
+          }
+        }
+      }
+      if (r < 4 * LK_KC) {
+        const int arr = r / LK_KC, p = p0 + r % LK_KC;
+        if (p < n) cp_async8(pix + r, s_pixptr[arr] + p);
+        else pix[r] = arr == 3 ? 1.0 : 0.0;
+      }
     }
     cp_async_commit();
   };
 
-  // phase A: W/G tiles of `panel`.  Branch-free over the four elements of a thread so that their
-  // dependent chains (load, products, reciprocal, ...) interleave.  Pixels beyond n are neutralised once per
-  // thread (a = 0, y = mu = omega2 = 0, v = 1  =>  w = g = 0, d = 1); samples beyond num_samples (last
-  // tile of a spectrum) compute on row 0 and are simply never written out - no per-element selects.
-  auto produce = [&](int panel) {
-    const int p = panel * LK_KC + pl;
-    const bool pv = p < n;
-    const double yp = pv ? s_pix[pl] : 0.0, mup = pv ? s_pix[LK_KC + pl] : 0.0;
-    const double omp = pv ? s_pix[2 * LK_KC + pl] : 0.0, vp = pv ? s_pix[3 * LK_KC + pl] : 1.0;
-    double a[LK_EPT];
-#pragma unroll
-    for (int e = 0; e < LK_EPT; ++e) a[e] = s_raw0[(ps0 + LK_PSTEP * e) * LK_KC + pl];
-    // absorption = product of the factors' profiles, left to right (dla_gp.py:370-386)
-    if (two_rows) {
-#pragma unroll
-      for (int e = 0; e < LK_EPT; ++e) a[e] = a[e] * s_raw1[(ps0 + LK_PSTEP * e) * LK_KC + pl];
+  // ---- the scalar chain of one W/G element, cut into slots ------------------------------------------------
+  // A thread owns two elements (pixel pl, samples ps0 and ps0 + 16) of every panel.  Their arithmetic
+  //     a = prod of the factors' profiles (dla_gp.py:370-386);  d = omega2 a^2 + v;  r = y - mu a;
+  //     w = a^2 / d;  g = a r / d;  q += r^2 / d;  prod d
+  // is 12 dependent FP64 operations each (11 for a single factor).  Slot 12 e + i is operation i of element e (one chain
+  // after the other measured 1.7 % faster than the two interleaved: fewer live registers); the main loop places one
+  // slot after every pair of DMMAs.  Samples beyond num_samples compute on row 0 and are never written out.
+  // PARN is the buffer parity of the panel being produced (compile time: every shared-memory address is a
+  // per-thread base plus an immediate).
+  double ca = 0.0, ca2 = 0.0, cd = 1.0, cr = 1.0, cer = 0.0, cres = 0.0, ct = 0.0;  // the chain in flight
+  double c_om = 0.0, c_v = 1.0, c_mu = 0.0, c_y = 0.0;
+  const double* raw_t = s_RAW + ps0 * LK_KC + pl;   // this thread's element 0 in RAW buffer 0
+  double* wg_t = s_WG + ps0 * LK_WSTRIDE + pl;      // ... and in W of buffer 0
+  auto scalar_slot = [&](const int slot, const int pn, auto parn_tag) {
+    constexpr int PARN = decltype(parn_tag)::value;
+    const int e = slot / 12, op = slot % 12;
+    const double* raw0 = raw_t + PARN * LK_RAW_DOUBLES + e * LK_PSTEP * LK_KC;
+    const double* pix = s_RAW + PARN * LK_RAW_DOUBLES + 2 * LK_TS * LK_KC + pl;
+    double* Wn = wg_t + PARN * 2 * LK_WG_DOUBLES + e * LK_PSTEP * LK_WSTRIDE;
+    switch (op) {
+      case 0: {
+        double a = raw0[0];
+        if (two_rows) a = mul_pinned(a, raw0[LK_TS * LK_KC]);
+        const int p = pn * LK_KC + pl;
+        if (num_rows > 2) {  // rare: dla_sample_log_likelihoods with more than two absorbers per sample
+          a = times_extra_factors(a, sp.cache, s_rows + ps0 + LK_PSTEP * e, num_rows, sp.ld, min(p, n - 1));
+          if (p >= n) a = 0.0;
+        }
+        if (sp.prod_out && p < n && ((live >> e) & 1u)) sp.prod_out[(size_t)(tile_s0 + ps0 + LK_PSTEP * e) * sp.ld + p] = a;
+        ca = a;
+        break;
+      }
+      case 1: ca2 = mul_pinned(ca, ca); break;
+      case 2:
+        c_om = pix[2 * LK_KC];
+        c_v = pix[3 * LK_KC];
+        cd = fma_pinned(c_om, ca2, c_v);  // dla_omega2 + v
+        break;
+      case 3:
+        c_y = pix[0];
+        c_mu = pix[LK_KC];
+        cres = fnma_pinned(c_mu, ca, c_y);  // y - dla_mu
+        cr = rcp_seed(cd);
+        break;
+      // 1 / d = r0 / (1 - e) = r0 (1 + e + e^2 + ...), e = 1 - d r0 <= 2^-20: the cubic term is below 2^-60
+      case 4: cer = fnma_pinned(cd, cr, 1.0); break;
+      case 5: cer = fma_pinned(cer, cer, cer); break;
+      case 6: {
+        cr = fma_pinned(cr, cer, cr);
+        // see fast_rcp: outside roughly [1e-290, 1e290] (and for 0, inf, NaN, negative d) keep the seed.  The test
+        // is on the exponent field with integer instructions - a DSETP would queue on the FP64 pipe like a DFMA
+        const unsigned hi = (unsigned)__double2hiint(cd);
+        if (!(hi - 0x03d00000u < 0x7c300000u - 0x03d00000u)) cr = rcp_seed(cd);
+        break;
+      }
+      case 7: dprod[e] = mul_pinned(dprod[e], cd); break;
+      case 8: Wn[0] = mul_pinned(ca2, cr); break;
+      case 9: ct = mul_pinned(cres, cr); break;
+      case 10: Wn[LK_WG_DOUBLES] = mul_pinned(ca, ct); break;
+      case 11: q_acc[e] = fma_pinned(cres, ct, q_acc[e]); break;
+      default: break;
     }
-    if (num_rows > 2) {  // rare: dla_sample_log_likelihoods with more than two absorbers per sample
-      const int pc = min(p, n - 1);
-#pragma unroll
-      for (int e = 0; e < LK_EPT; ++e)
-        for (int r = 2; r < num_rows; ++r)
-          a[e] = a[e] * sp.cache[(size_t)s_rows[r * LK_TS + ps0 + LK_PSTEP * e] * sp.ld + pc];
-    }
-    if (sp.prod_out && pv) {
-#pragma unroll
-      for (int e = 0; e < LK_EPT; ++e)
-        if ((live >> e) & 1u) sp.prod_out[(size_t)(tile_s0 + ps0 + LK_PSTEP * e) * sp.ld + p] = a[e];
-    }
-    // the four elements advance in lock step (one loop per operation): four independent dependency
-    // chains in flight instead of one after the other
-    double a2[LK_EPT], d[LK_EPT], r0[LK_EPT], er[LK_EPT], inv[LK_EPT], res[LK_EPT], t[LK_EPT];
-#pragma unroll
-    for (int e = 0; e < LK_EPT; ++e) a[e] = pv ? a[e] : 0.0;  // pad columns of the profile rows hold no data
-#pragma unroll
-    for (int e = 0; e < LK_EPT; ++e) a2[e] = a[e] * a[e];
-#pragma unroll
-    for (int e = 0; e < LK_EPT; ++e) d[e] = fma(omp, a2[e], vp);          // dla_omega2 + v
-#pragma unroll
-    for (int e = 0; e < LK_EPT; ++e) asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r0[e]) : "d"(d[e]));
-#pragma unroll
-    for (int e = 0; e < LK_EPT; ++e) res[e] = fma(-mup, a[e], yp);        // y - dla_mu
-#pragma unroll
-    for (int e = 0; e < LK_EPT; ++e) er[e] = fma(-d[e], r0[e], 1.0);
-#pragma unroll
-    for (int e = 0; e < LK_EPT; ++e) inv[e] = fma(r0[e], er[e], r0[e]);
-#pragma unroll
-    for (int e = 0; e < LK_EPT; ++e) er[e] = fma(-d[e], inv[e], 1.0);
-#pragma unroll
-    for (int e = 0; e < LK_EPT; ++e) inv[e] = fma(inv[e], er[e], inv[e]);
-#pragma unroll
-    for (int e = 0; e < LK_EPT; ++e) {
-      // see fast_rcp: outside roughly [1e-290, 1e290] (and for 0, inf, NaN, negative d) keep the seed.  The test
-      // is on the exponent field with integer instructions - a DSETP would queue on the FP64 pipe like a DFMA
-      const unsigned hi = (unsigned)__double2hiint(d[e]);
-      inv[e] = (hi - 0x03d00000u < 0x7c300000u - 0x03d00000u) ? inv[e] : r0[e];
-    }
-#pragma unroll
-    for (int e = 0; e < LK_EPT; ++e) t[e] = res[e] * inv[e];
-#pragma unroll
-    for (int e = 0; e < LK_EPT; ++e) {
-      const int s = ps0 + LK_PSTEP * e;
-      s_W[s * LK_WSTRIDE + pl] = a2[e] * inv[e];
-      s_G[s * LK_WSTRIDE + pl] = a[e] * t[e];
-    }
-#pragma unroll
-    for (int e = 0; e < LK_EPT; ++e) q_acc[e] = fma(res[e], t[e], q_acc[e]);
-#pragma unroll
-    for (int e = 0; e < LK_EPT; ++e) dprod[e] *= d[e];
   };
+  constexpr int LK_SLOTS = 12 * LK_EPT;  // 24
 
   // ---- MMA role: warp (rq, cq) owns samples 16 rq .. 16 rq + 15 and 7 or 8 column blocks -----------
   //   rq even : blocks [0,8) [8,15) [15,23) [23,30)      rq odd : blocks [0,7) [7,15) [15,22) [22,30)
   // Blocks >= 27 are the projection part (A = G).  Local blocks 0..3 always take A = W, local block 4
-  // and local blocks 5..7 read A through pointers (W or G), so all warps run one instruction stream
+  // and local blocks 5..7 read A through offsets (W or G), so all warps run one instruction stream
   // with no predicated DMMA (a predicated-off DMMA still occupies its pipe slot); the eighth block
   // sits behind a warp-uniform branch.
   const int grp = lane >> 2;      // DMMA groupID
@@ -382,78 +452,86 @@ sample_likelihood_kernel(const LikelihoodSpectrum* __restrict__ specs) {
   const bool odd = (rq & 1) != 0;
   const int first = !odd ? (cq == 0 ? 0 : cq == 1 ? 8 : cq == 2 ? 15 : 23) : (cq == 0 ? 0 : cq == 1 ? 7 : cq == 2 ? 15 : 22);
   const bool has_eighth = ((cq + (odd ? 1 : 0)) & 1) == 0;
-  const bool g4 = first + 4 >= LK_NBLK_PAIR, g5 = first + 5 >= LK_NBLK_PAIR;
   const int stage_rank = (rq * 2 + (cq >> 1)) * 32 + lane;  // rank among the threads of the 7-block warps
+  const double* arow = s_WG + (rq * 16 + grp) * LK_WSTRIDE + tig;                     // A fragment base, buffer 0
+  const double* a4row = arow + (first + 4 >= LK_NBLK_PAIR ? LK_WG_DOUBLES : 0);        // W or G
+  const double* a5row = arow + (first + 5 >= LK_NBLK_PAIR ? LK_WG_DOUBLES : 0);
+  const double* brow = s_main + tig * LK_PSTRIDE + first * 8 + grp;                    // B fragment base, stage 0
   double acc[LK_MB][LK_NB_MAX][2];
 #pragma unroll
   for (int m = 0; m < LK_MB; ++m)
 #pragma unroll
     for (int nb = 0; nb < LK_NB_MAX; ++nb) acc[m][nb][0] = acc[m][nb][1] = 0.0;
 
-  // phase B: DMMAs of `panel`
-  auto consume = [&](int panel, bool stage_next) {
-    const int pstage = panel & (LK_PSTAGES - 1);
-    const double* Ps = s_main + pstage * LK_PANEL_DOUBLES;
-    mbar_wait(bar_base + 8u * pstage, (panel / LK_PSTAGES) & 1);  // basis panel landed
-    const int aoff = (rq * 16 + grp) * LK_WSTRIDE + tig;
-    const double* arow = s_W + aoff;
-    const double* a4row = (g4 ? s_G : s_W) + aoff;
-    const double* a5row = (g5 ? s_G : s_W) + aoff;
-    const double* brow = Ps + tig * LK_PSTRIDE + first * 8 + grp;
+  // One panel of parity PAR: its DMMAs with, when PRODUCE, the scalar slots of panel + 1 threaded through them
+  // (28 steps of two DMMAs in the seven common blocks x four k-steps, 24 slots); STAGE: the 7-block warps
+  // request the inputs of panel + 2.
+  auto run_panel = [&](const int panel, auto par_tag, auto produce_tag, auto stage_tag) {
+    constexpr int PAR = decltype(par_tag)::value;
+    constexpr bool PRODUCE = decltype(produce_tag)::value, STAGE = decltype(stage_tag)::value;
+    static_assert(LK_PSTAGES == 2, "basis stage == panel parity");
+    if (tid == 0 && PRODUCE) issue_panel(panel + 1);              // its stage was drained by the DMMAs of panel - 1
+    mbar_wait(bar_base + 8u * PAR, (panel >> 1) & 1);             // basis panel landed
+    constexpr int WOFF = PAR * 2 * LK_WG_DOUBLES, POFF = PAR * LK_PANEL_DOUBLES;
 #pragma unroll
-    for (int kb = 0; kb < LK_KC / 4; ++kb) {
-      // the cp.async requests of the next panel go out after the first DMMAs, so that their address
-      // arithmetic runs while the tensor pipe already has work queued; they are issued by the warps that
-      // own 7 column blocks, which otherwise idle at the barrier while the 8-block warps finish
-      if (kb == 1 && stage_next && !has_eighth) stage_panel(panel + 1, stage_rank, (LK_WARPS / 2) * 32);
-      double a[LK_MB];
+    for (int j = 0; j < 7 * (LK_KC / 4); ++j) {
+      const int kb = j / 7, nb = j % 7;
+      // the cp.async requests go out after the first DMMAs, so that the pipe already has work queued
+      if (STAGE && j == 7 && !has_eighth) stage_panel(panel + 2, par_tag, stage_rank, (LK_WARPS / 2) * 32);
+      const double* ar = nb < 4 ? arow : nb == 4 ? a4row : a5row;
+      const double b = brow[POFF + kb * 4 * LK_PSTRIDE + nb * 8];
 #pragma unroll
-      for (int m = 0; m < LK_MB; ++m) a[m] = arow[m * 8 * LK_WSTRIDE + kb * 4];
-#pragma unroll
-      for (int nb = 0; nb < 4; ++nb) {
-        const double b = brow[kb * 4 * LK_PSTRIDE + nb * 8];
-#pragma unroll
-        for (int m = 0; m < LK_MB; ++m) dmma884(acc[m][nb][0], acc[m][nb][1], a[m], b);
-      }
-#pragma unroll
-      for (int m = 0; m < LK_MB; ++m) a[m] = a4row[m * 8 * LK_WSTRIDE + kb * 4];
-      {
-        const double b = brow[kb * 4 * LK_PSTRIDE + 4 * 8];
-#pragma unroll
-        for (int m = 0; m < LK_MB; ++m) dmma884(acc[m][4][0], acc[m][4][1], a[m], b);
-      }
-#pragma unroll
-      for (int m = 0; m < LK_MB; ++m) a[m] = a5row[m * 8 * LK_WSTRIDE + kb * 4];
-#pragma unroll
-      for (int nb = 5; nb < 7; ++nb) {
-        const double b = brow[kb * 4 * LK_PSTRIDE + nb * 8];
-#pragma unroll
-        for (int m = 0; m < LK_MB; ++m) dmma884(acc[m][nb][0], acc[m][nb][1], a[m], b);
-      }
+      for (int m = 0; m < LK_MB; ++m)
+        dmma884_pinned(acc[m][nb][0], acc[m][nb][1], ar[WOFF + m * 8 * LK_WSTRIDE + kb * 4], b);
+      if (PRODUCE && j < LK_SLOTS) scalar_slot(j, panel + 1, std::integral_constant<int, 1 - PAR>{});
     }
     if (has_eighth) {
 #pragma unroll
       for (int kb = 0; kb < LK_KC / 4; ++kb) {
-        const double b = brow[kb * 4 * LK_PSTRIDE + 7 * 8];
+        const double b = brow[POFF + kb * 4 * LK_PSTRIDE + 7 * 8];
 #pragma unroll
         for (int m = 0; m < LK_MB; ++m)
-          dmma884(acc[m][7][0], acc[m][7][1], a5row[m * 8 * LK_WSTRIDE + kb * 4], b);
+          dmma884_pinned(acc[m][7][0], acc[m][7][1], a5row[WOFF + m * 8 * LK_WSTRIDE + kb * 4], b);
       }
     }
+    cp_async_wait_all();
+    __syncthreads();
   };
+  using P0 = std::integral_constant<int, 0>;
+  using P1 = std::integral_constant<int, 1>;
 
-  // ---- main loop: phase A | barrier | phase B | barrier --------------------------------------------------
-  stage_panel(0, tid, LK_THREADS);
+  // ---- prologue: inputs of panels 0 and 1, W/G of panel 0 ---------------------------------------------------
+  stage_panel(0, P0{}, tid, LK_THREADS);
+  if (npanels > 1) stage_panel(1, P1{}, tid, LK_THREADS);
   cp_async_wait_all();
   __syncthreads();
-  for (int panel = 0; panel < npanels; ++panel) {
-    if (tid == 0 && panel + 1 < npanels) issue_panel(panel + 1);  // its stage was drained by phase B of panel - 1
-    produce(panel);
-    __syncthreads();                                              // W/G complete, staged inputs consumed
-    consume(panel, panel + 1 < npanels);                          // stages the next panel's inputs underneath the DMMAs
-    if ((panel & 3) == 3) renorm();
-    cp_async_wait_all();
-    __syncthreads();                                              // W/G and the basis stage are free, inputs staged
+#pragma unroll
+  for (int slot = 0; slot < LK_SLOTS; ++slot) scalar_slot(slot, 0, P0{});
+  __syncthreads();
+
+  // ---- main loop: one barrier per panel, two panels per trip (buffer parities are compile-time) -------------------
+  // panel p: DMMAs read W/G[p & 1] and basis stage p & 1; the scalar slots read RAW[(p + 1) & 1] and write
+  // W/G[(p + 1) & 1]; cp.async fills RAW[p & 1] with the inputs of p + 2; TMA fills the other basis stage
+  // with p + 1.  The barrier at the end of the panel publishes all of it.
+  {
+    int panel = 0;
+    for (; panel + 3 < npanels; panel += 2) {   // both panels have successors to produce and to stage
+      run_panel(panel, P0{}, std::true_type{}, std::true_type{});
+      run_panel(panel + 1, P1{}, std::true_type{}, std::true_type{});
+      if (panel & 2) renorm();
+    }
+    renorm();
+    const int left = npanels - panel;           // 1, 2 or 3
+    if (left == 3) {
+      run_panel(panel, P0{}, std::true_type{}, std::true_type{});
+      run_panel(panel + 1, P1{}, std::true_type{}, std::false_type{});
+      run_panel(panel + 2, P0{}, std::false_type{}, std::false_type{});
+    } else if (left == 2) {
+      run_panel(panel, P0{}, std::true_type{}, std::false_type{});
+      run_panel(panel + 1, P1{}, std::false_type{}, std::false_type{});
+    } else {
+      run_panel(panel, P0{}, std::false_type{}, std::false_type{});
+    }
   }
 
   // per-sample scalar sums: reduce over the pixel lanes of the panel
