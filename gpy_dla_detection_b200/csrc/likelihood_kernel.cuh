@@ -205,6 +205,17 @@ __device__ __forceinline__ void cp_async16_zfill(void* smem_dst, const void* gme
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;\n" ::: "memory"); }
 
+// 1 / sqrt(x) for the Cholesky pivots: MUFU.RSQ64H seed y0 and one cubic correction y0 (1 + e/2 + 3 e^2/8),
+// e = 1 - x y0^2 <= 2^-20 (5 dependent FP64 operations; the library routine issues twice as many and a branch).
+// Pivots of I + M'D^-1 M are >= 1; zero, negative or NaN pivots (NaN input) come out as inf / NaN and poison the sample.
+__device__ __forceinline__ double fast_rsqrt(double x) {
+  double y0;
+  asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y0) : "d"(x));
+  const double e = fma(-(x * y0), y0, 1.0);
+  const double p = fma(e, 0.375, 0.5) * e;
+  return fma(y0, p, y0);
+}
+
 // factors 2 .. num_rows - 1 of a sample (dla_sample_log_likelihoods with more than two absorbers per sample):
 // rare, kept out of line so that the main loop stays small
 __device__ __noinline__ double times_extra_factors(double a, const double* cache, const int32_t* rows_of_sample,
@@ -233,7 +244,7 @@ __device__ __forceinline__ double fast_rcp(double d) {
 //   RAW        : 2 buffers x { profile-row panels of factor 0 and factor 1 [32][16] each, y, mu, omega2, v [4][16] }
 //                (read by the scalar slots / filled by cp.async for the panel after)           17 408 B
 //   E          : epilogue matrix [240][33], overlays the above                          63 360 B
-//   AUX        : per-sample sums [32][2], profile row indices [8][32], row pointers [2][32] + 4, 2 mbarriers
+//   AUX        : per-sample sums [32][3], profile row indices [8][32], row pointers [2][32] + 4, 2 mbarriers
 constexpr int LK_PANEL_DOUBLES = LK_KC * LK_PSTRIDE;               // 3904
 constexpr int LK_WG_DOUBLES = LK_TS * LK_WSTRIDE;                  // 640
 constexpr uint32_t LK_PANEL_BYTES = LK_PANEL_DOUBLES * sizeof(double);  // 31 232
@@ -241,7 +252,7 @@ constexpr int LK_RAW_DOUBLES = 2 * LK_TS * LK_KC + 4 * LK_KC;       // 1088
 constexpr int LK_RING_DOUBLES = LK_PSTAGES * LK_PANEL_DOUBLES + 2 * (2 * LK_WG_DOUBLES + LK_RAW_DOUBLES);  // 12 544
 constexpr int LK_EP_DOUBLES = LK_NCOLS * LK_EP_STRIDE;             // 7920
 constexpr int LK_MAIN_DOUBLES = LK_RING_DOUBLES > LK_EP_DOUBLES ? LK_RING_DOUBLES : LK_EP_DOUBLES;
-constexpr size_t LK_AUX_BYTES = LK_TS * 2 * sizeof(double) + LK_MAX_ROWS * LK_TS * sizeof(int32_t) +
+constexpr size_t LK_AUX_BYTES = LK_TS * 3 * sizeof(double) + LK_MAX_ROWS * LK_TS * sizeof(int32_t) +
                                 (2 * LK_TS + 4) * sizeof(void*) + LK_PSTAGES * sizeof(uint64_t);
 constexpr size_t LK_SMEM_BYTES = (size_t)LK_MAIN_DOUBLES * sizeof(double) + LK_AUX_BYTES;
 static_assert(LK_PANEL_BYTES % 128 == 0, "TMA alignment");
@@ -259,8 +270,8 @@ sample_likelihood_kernel(const LikelihoodSpectrum* __restrict__ specs) {
   double* s_WG = s_main + LK_PSTAGES * LK_PANEL_DOUBLES;  // 2 buffers x { W [32][20], G [32][20] }
   double* s_RAW = s_WG + 2 * 2 * LK_WG_DOUBLES;           // 2 buffers x { factor-0 rows [32][16], factor-1 rows [32][16],
                                                           //               y, mu, omega2, v [4][16] } of a staged panel
-  double* s_sums = s_main + LK_MAIN_DOUBLES;                          // [32][2] : sum r^2/d, sum log d
-  int32_t* s_rows = reinterpret_cast<int32_t*>(s_sums + LK_TS * 2);   // [num_rows][32]
+  double* s_sums = s_main + LK_MAIN_DOUBLES;                          // [32][3] : sum r^2/d; mantissa product and exponent sum of prod d
+  int32_t* s_rows = reinterpret_cast<int32_t*>(s_sums + LK_TS * 3);   // [num_rows][32]
   const double** s_ptr0 = reinterpret_cast<const double**>(s_rows + LK_MAX_ROWS * LK_TS);  // [32] factor-0 row of each sample
   const double** s_ptr1 = s_ptr0 + LK_TS;                                                    // [32] factor-1 row
   const double** s_pixptr = s_ptr1 + LK_TS;                                                  // y, mu, omega2, v
@@ -538,16 +549,23 @@ sample_likelihood_kernel(const LikelihoodSpectrum* __restrict__ specs) {
   renorm();
 #pragma unroll
   for (int e = 0; e < LK_EPT; ++e) {
+    // sum log d = ln2 * (sum of the exponents) + log(product of the renormalised mantissa products): the 16 lanes'
+    // products (each in [1, 2)) are multiplied here and the one logarithm per sample is taken together with the
+    // pivots' in the Cholesky phase (a log per lane was 80 FP64 instructions per thread in a phase that crawls
+    // next to the other CTA's DMMAs).  A non-positive or NaN product poisons the sample like log() would.
     double q = q_acc[e];
-    double l = fma((double)esum[e], LK_LN2, log(dprod[e]));
+    double dp = dprod[e] > 0.0 ? dprod[e] : __longlong_as_double(0x7ff8000000000000ll);
+    int es = esum[e];
 #pragma unroll
     for (int off = (LK_KC < 32 ? LK_KC : 32) / 2; off > 0; off >>= 1) {
       q += __shfl_xor_sync(0xffffffffu, q, off);
-      l += __shfl_xor_sync(0xffffffffu, l, off);
+      dp *= __shfl_xor_sync(0xffffffffu, dp, off);
+      es += __shfl_xor_sync(0xffffffffu, es, off);
     }
     if (pl == 0) {
-      s_sums[(ps0 + LK_PSTEP * e) * 2] = q;
-      s_sums[(ps0 + LK_PSTEP * e) * 2 + 1] = l;
+      s_sums[(ps0 + LK_PSTEP * e) * 3] = q;
+      s_sums[(ps0 + LK_PSTEP * e) * 3 + 1] = dp;
+      s_sums[(ps0 + LK_PSTEP * e) * 3 + 2] = (double)es;
     }
   }
 
@@ -633,7 +651,7 @@ sample_likelihood_kernel(const LikelihoodSpectrum* __restrict__ specs) {
       // the pivot is the x of row j itself
       const double piv = __shfl_sync(0xffffffffu, j < 8 ? x0 : j < 16 ? x1 : x2, owner);
       piv_prod *= piv;
-      const double inv = rsqrt(piv);
+      const double inv = fast_rsqrt(piv);
       if (j < 8) r0[j] = x0 * inv;    // rows below j become column j of L (the pivot row's own entry is not used again)
       if (j < 16) r1[j] = x1 * inv;
       r2[j] = x2 * inv;
@@ -643,8 +661,8 @@ sample_likelihood_kernel(const LikelihoodSpectrum* __restrict__ specs) {
       double zz0 = 0.0, zz1 = 0.0;
 #pragma unroll
       for (int k = 0; k < LK_K; k += 2) { zz0 = fma(r2[k], r2[k], zz0); zz1 = fma(r2[k + 1], r2[k + 1], zz1); }
-      const double quad = s_sums[s * 2] - (zz0 + zz1);
-      const double log_det = s_sums[s * 2 + 1] + log(piv_prod);  // sum log d + 2 sum log L_ii
+      const double quad = s_sums[s * 3] - (zz0 + zz1);
+      const double log_det = fma(s_sums[s * 3 + 2], LK_LN2, log(s_sums[s * 3 + 1] * piv_prod));  // sum log d + 2 sum log L_ii
       sp.out[tile_s0 + s] = -0.5 * (quad + log_det + (double)n * LK_LOG_2PI);
     }
   }
