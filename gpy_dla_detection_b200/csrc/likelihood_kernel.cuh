@@ -184,6 +184,9 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
       "DONE:\n"
       "}\n" ::"r"(bar), "r"(parity) : "memory");
 }
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
 __device__ __forceinline__ void tma_bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
@@ -197,10 +200,6 @@ __device__ __forceinline__ void cp_async8(void* smem_dst, const void* gmem_src) 
 __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src) {
   const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(d), "l"(gmem_src) : "memory");
-}
-__device__ __forceinline__ void cp_async16_zfill(void* smem_dst, const void* gmem_src, int src_bytes) {
-  const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(d), "l"(gmem_src), "r"(src_bytes) : "memory");
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;\n" ::: "memory"); }
@@ -224,17 +223,18 @@ __device__ __noinline__ double times_extra_factors(double a, const double* cache
   return a;
 }
 
-// 1/d for the operand tiles: MUFU.RCP64H seed (SFU, not the FP64 pipe) + two Newton steps (4 DFMA),
-// <= 1 ulp from the IEEE quotient.  Branch-free, so the four elements of a thread interleave: outside
-// [1e-290, 1e290] (0, inf, NaN, negative: never produced by a valid spectrum) the seed itself is
-// returned, which has the IEEE special-value behaviour (1/inf = 0, 1/0 = inf, NaN stays NaN).
+// 1/d as the scalar slots of sample_likelihood_kernel compute it (operations 4-6 of a chain; written out here as
+// one function for reference and for the unit test of the formula): MUFU.RCP64H seed r0 (SFU, not the FP64 pipe,
+// relative error e = 1 - d r0 <= 2^-20) and one cubic correction r0 (1 + e + e^2): 3 dependent DFMA, truncation
+// error e^3 < 2^-60, <= 1 ulp from the IEEE quotient.  Outside [1e-290, 1e290] (0, inf, NaN, negative: never
+// produced by a valid spectrum) the seed itself is returned, which has the IEEE special-value behaviour
+// (1/inf = 0, 1/0 = inf, NaN stays NaN).
 __device__ __forceinline__ double fast_rcp(double d) {
   double r0;
   asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r0) : "d"(d));
   double e = fma(-d, r0, 1.0);
-  double r = fma(r0, e, r0);
-  e = fma(-d, r, 1.0);
-  r = fma(r, e, r);
+  e = fma(e, e, e);
+  const double r = fma(r0, e, r0);
   return (d > 1e-290 && d < 1e290) ? r : r0;
 }
 
@@ -253,7 +253,7 @@ constexpr int LK_RING_DOUBLES = LK_PSTAGES * LK_PANEL_DOUBLES + 2 * (2 * LK_WG_D
 constexpr int LK_EP_DOUBLES = LK_NCOLS * LK_EP_STRIDE;             // 7920
 constexpr int LK_MAIN_DOUBLES = LK_RING_DOUBLES > LK_EP_DOUBLES ? LK_RING_DOUBLES : LK_EP_DOUBLES;
 constexpr size_t LK_AUX_BYTES = LK_TS * 3 * sizeof(double) + LK_MAX_ROWS * LK_TS * sizeof(int32_t) +
-                                (2 * LK_TS + 4) * sizeof(void*) + LK_PSTAGES * sizeof(uint64_t);
+                                (2 * LK_TS + 4) * sizeof(void*) + (LK_PSTAGES + 2) * sizeof(uint64_t);
 constexpr size_t LK_SMEM_BYTES = (size_t)LK_MAIN_DOUBLES * sizeof(double) + LK_AUX_BYTES;
 static_assert(LK_PANEL_BYTES % 128 == 0, "TMA alignment");
 
@@ -283,6 +283,16 @@ sample_likelihood_kernel(const LikelihoodSpectrum* __restrict__ specs) {
   const int npanels = (n + LK_KC - 1) / LK_KC;
   const int num_rows = sp.num_rows;
   const uint32_t bar_base = (uint32_t)__cvta_generic_to_shared(s_mbar);
+  // Split barriers between the warps of the CTA (one arrival per warp, mbarrier phase = panel): `full` completes when
+  // every warp has stored its W/G entries of the next panel and its staged inputs have landed; `empty` when every
+  // warp has issued its last DMMA of the panel.  A warp waits for `full` at the top of a panel and for the previous
+  // panel's `empty` only before its first store (a third of the way in), so the warps may drift apart by that much
+  // instead of meeting at a CTA barrier every panel (the barrier was 9 % of all warp stall samples).
+  const uint32_t bar_full = bar_base + 8u * LK_PSTAGES, bar_empty = bar_full + 8u;
+  auto warp_arrive = [&](uint32_t bar) {
+    __syncwarp();
+    if (lane == 0) mbar_arrive(bar);
+  };
 
   // basis panel `panel` -> its ring stage (one thread; completion is the stage's mbarrier)
   auto issue_panel = [&](int panel) {
@@ -309,6 +319,8 @@ sample_likelihood_kernel(const LikelihoodSpectrum* __restrict__ specs) {
   if (tid == 0) {
 #pragma unroll
     for (int s = 0; s < LK_PSTAGES; ++s) mbar_init(bar_base + 8u * s, 1);
+    mbar_init(bar_full, LK_WARPS);
+    mbar_init(bar_empty, LK_WARPS);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     issue_panel(0);
   }
@@ -481,20 +493,29 @@ sample_likelihood_kernel(const LikelihoodSpectrum* __restrict__ specs) {
     constexpr int PAR = decltype(par_tag)::value;
     constexpr bool PRODUCE = decltype(produce_tag)::value, STAGE = decltype(stage_tag)::value;
     static_assert(LK_PSTAGES == 2, "basis stage == panel parity");
-    if (tid == 0 && PRODUCE) issue_panel(panel + 1);              // its stage was drained by the DMMAs of panel - 1
+    mbar_wait(bar_full, PAR);                                     // W/G of this panel written, inputs of the next landed
     mbar_wait(bar_base + 8u * PAR, (panel >> 1) & 1);             // basis panel landed
     constexpr int WOFF = PAR * 2 * LK_WG_DOUBLES, POFF = PAR * LK_PANEL_DOUBLES;
 #pragma unroll
     for (int j = 0; j < 7 * (LK_KC / 4); ++j) {
       const int kb = j / 7, nb = j % 7;
-      // the cp.async requests go out after the first DMMAs, so that the pipe already has work queued
-      if (STAGE && j == 7 && !has_eighth) stage_panel(panel + 2, par_tag, stage_rank, (LK_WARPS / 2) * 32);
+      if (j == 7) {
+        // From here on this panel overwrites what panel - 1 read: the other W/G buffer (first store in slot 8), the
+        // other basis stage (TMA) and the RAW buffer of the inputs of panel (cp.async).
+        if (panel > 0) mbar_wait(bar_empty, 1 - PAR);
+        if (tid == 0 && PRODUCE) issue_panel(panel + 1);
+        if (STAGE && !has_eighth) stage_panel(panel + 2, par_tag, stage_rank, (LK_WARPS / 2) * 32);
+      }
       const double* ar = nb < 4 ? arow : nb == 4 ? a4row : a5row;
       const double b = brow[POFF + kb * 4 * LK_PSTRIDE + nb * 8];
 #pragma unroll
       for (int m = 0; m < LK_MB; ++m)
         dmma884_pinned(acc[m][nb][0], acc[m][nb][1], ar[WOFF + m * 8 * LK_WSTRIDE + kb * 4], b);
       if (PRODUCE && j < LK_SLOTS) scalar_slot(j, panel + 1, std::integral_constant<int, 1 - PAR>{});
+      if (PRODUCE && j == LK_SLOTS - 2) {  // the warp's last W/G store is behind it: publish (and its staged inputs)
+        cp_async_wait_all();
+        warp_arrive(bar_full);
+      }
     }
     if (has_eighth) {
 #pragma unroll
@@ -505,8 +526,7 @@ sample_likelihood_kernel(const LikelihoodSpectrum* __restrict__ specs) {
           dmma884_pinned(acc[m][7][0], acc[m][7][1], a5row[WOFF + m * 8 * LK_WSTRIDE + kb * 4], b);
       }
     }
-    cp_async_wait_all();
-    __syncthreads();
+    warp_arrive(bar_empty);                                       // this warp is done reading panel's W/G, basis stage, inputs
   };
   using P0 = std::integral_constant<int, 0>;
   using P1 = std::integral_constant<int, 1>;
@@ -518,7 +538,7 @@ sample_likelihood_kernel(const LikelihoodSpectrum* __restrict__ specs) {
   __syncthreads();
 #pragma unroll
   for (int slot = 0; slot < LK_SLOTS; ++slot) scalar_slot(slot, 0, P0{});
-  __syncthreads();
+  warp_arrive(bar_full);
 
   // ---- main loop: one barrier per panel, two panels per trip (buffer parities are compile-time) -------------------
   // panel p: DMMAs read W/G[p & 1] and basis stage p & 1; the scalar slots read RAW[(p + 1) & 1] and write
@@ -569,7 +589,8 @@ sample_likelihood_kernel(const LikelihoodSpectrum* __restrict__ specs) {
     }
   }
 
-  // ---- accumulators -> E[col][sample] (overlays the ring; the last barrier of the loop freed it) --------
+  // ---- accumulators -> E[col][sample] (overlays the ring once every warp has left the loop) -------------
+  __syncthreads();
   double* E = s_main;
   {
     const int count = has_eighth ? 8 : 7;
