@@ -499,12 +499,15 @@ sample_likelihood_kernel(const LikelihoodSpectrum* __restrict__ specs) {
 #pragma unroll
     for (int j = 0; j < 7 * (LK_KC / 4); ++j) {
       const int kb = j / 7, nb = j % 7;
+      // The inputs of panel + 2 go into the RAW buffer that held those of panel: every warp read them in slots 0-15
+      // of panel - 1 and has passed slot 22 (`full`), so the buffer is free; the requests go out after the first
+      // DMMAs, so that the pipe already has work queued, and have most of the panel to land.
+      if (STAGE && j == 1 && !has_eighth) stage_panel(panel + 2, par_tag, stage_rank, (LK_WARPS / 2) * 32);
       if (j == 7) {
-        // From here on this panel overwrites what panel - 1 read: the other W/G buffer (first store in slot 8), the
-        // other basis stage (TMA) and the RAW buffer of the inputs of panel (cp.async).
+        // From here on this panel overwrites what panel - 1 read to its end: the other W/G buffer (first store in
+        // slot 8) and the other basis stage (TMA).
         if (panel > 0) mbar_wait(bar_empty, 1 - PAR);
         if (tid == 0 && PRODUCE) issue_panel(panel + 1);
-        if (STAGE && !has_eighth) stage_panel(panel + 2, par_tag, stage_rank, (LK_WARPS / 2) * 32);
       }
       const double* ar = nb < 4 ? arow : nb == 4 ? a4row : a5row;
       const double b = brow[POFF + kb * 4 * LK_PSTRIDE + nb * 8];
