@@ -24,12 +24,13 @@
 //     their own instruction streams are the think time of that queue.
 // So every warp runs ONE instruction stream per panel: the DMMAs of panel p with the scalar arithmetic that
 // produces the W / G operand tiles of panel p + 1 threaded through them, and as little else as possible:
-//   * a CTA of 8 warps owns 32 samples and walks the pixels in 16-pixel panels, one barrier per panel, two
+//   * a CTA of 8 warps owns 32 samples and walks the pixels in 16-pixel panels (no CTA barrier in the loop: two split
+//     mbarriers, full / empty, one arrival per warp, waited a quarter of a panel after the arrivals), two
 //     panels per loop trip so that all buffer parities are compile-time and every shared-memory address is a
 //     per-thread base plus an immediate; two CTAs share an SM;
 //   * scalar work: every thread turns 2 profile-cache elements (product of up to 8 absorber factors,
 //     dla_gp.py:370-386) into W / G entries - MUFU-seeded reciprocal with one cubic correction,
-//     integer-renormalised running product for sum log d (one log per lane per tile), no validity selects
+//     integer-renormalised running product for sum log d (one log per sample per tile), no validity selects
 //     (the last panel is staged with neutral values beyond n);
 //   * DMMA work: warp (rq, cq) owns 16 samples x 7 or 8 of the 30 column blocks, sized [8,7,8,7] / [7,8,7,8]
 //     by row half so that the two warps a CTA has on every SM sub-partition issue 30 DMMAs per 4 pixels: no
@@ -543,10 +544,10 @@ sample_likelihood_kernel(const LikelihoodSpectrum* __restrict__ specs) {
   for (int slot = 0; slot < LK_SLOTS; ++slot) scalar_slot(slot, 0, P0{});
   warp_arrive(bar_full);
 
-  // ---- main loop: one barrier per panel, two panels per trip (buffer parities are compile-time) -------------------
+  // ---- main loop: two panels per trip (buffer parities are compile-time) ------------------------------------------
   // panel p: DMMAs read W/G[p & 1] and basis stage p & 1; the scalar slots read RAW[(p + 1) & 1] and write
   // W/G[(p + 1) & 1]; cp.async fills RAW[p & 1] with the inputs of p + 2; TMA fills the other basis stage
-  // with p + 1.  The barrier at the end of the panel publishes all of it.
+  // with p + 1.  The `full` and `empty` mbarriers order all of it between the warps.
   {
     int panel = 0;
     for (; panel + 3 < npanels; panel += 2) {   // both panels have successors to produce and to stage
