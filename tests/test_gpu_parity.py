@@ -543,3 +543,36 @@ def test_catalogue_unpaired_subdla_offsets(gpu, O):
         assert H.ll_err(out["sample_log_likelihoods_dla"][q], ref["sample_log_likelihoods_dla"]) < LL_RTOL
         assert np.array_equal(out["base_sample_inds"][q].T, ref["base_sample_inds"])
         assert np.max(np.abs(out["log_posteriors"][q] - ref["log_posteriors"])) < EV_ATOL
+
+
+def test_likelihood_kernel_panel_tails_and_many_absorbers(gpu, O):
+    """sample_likelihood_kernel at pixel counts around every panel boundary (1 .. 5 panels of 16 pixels, partial
+    last panels, masked pixels), sample counts that leave a partial last tile, and 1 .. 5 absorbers per sample
+    (more than two factors take the out-of-line path), against the oracle's sample_log_likelihood_k_dlas
+    (dla_gp.py:311-396)."""
+    from gpy_dla_detection_b200 import log_posterior_mcmc as M
+
+    rng = np.random.default_rng(5)
+    k, W = 20, 70
+    worst = 0.0
+    for n_u in [1, 2, 3, 7, 15, 16, 17, 31, 32, 33, 47, 48, 49, 63, 64, 65, 80, 81]:
+        padded = 10 ** (3.6 + 1e-4 * np.arange(n_u + 6))           # observed wavelengths, BOSS pixel scale
+        keep = rng.random(n_u) > 0.1
+        keep[rng.integers(n_u)] = True
+        n = int(keep.sum())
+        prep = {
+            "padded_wavelengths": padded, "mask_ind": keep,
+            "this_mu": 1.0 + 0.1 * rng.standard_normal(n), "this_M": 0.2 * rng.standard_normal((n, k)),
+            "this_omega2": rng.uniform(0.01, 0.1, n), "y": 1.0 + 0.3 * rng.standard_normal(n),
+            "v": rng.uniform(0.01, 0.2, n),
+        }
+        z_mid = padded[3 + n_u // 2] / 1215.6701 - 1.0
+        for kd in (1, 2, 3, 5):
+            zz = z_mid + 0.01 * rng.standard_normal((W, kd))
+            nn = 10 ** rng.uniform(19.5, 21.5, (W, kd))
+            got = M.sample_log_likelihoods(zz, nn, prep["y"], prep["v"], padded, prep["this_mu"], prep["this_M"],
+                                           prep["this_omega2"], ~keep, np.ones(n_u, bool), 3)
+            ref = np.array([O.sample_log_likelihood_k_dlas(prep, zz[i], nn[i], 3) for i in range(W)])
+            assert np.all(np.isfinite(got)), (n_u, kd)
+            worst = max(worst, H.ll_err(got, ref))
+    assert worst < 1e-9, worst  # |d ll| / max(|ll|, 1), the tolerance of the full-size tests
