@@ -287,7 +287,7 @@ sample_likelihood_kernel(const LikelihoodSpectrum* __restrict__ specs) {
   // Split barriers between the warps of the CTA (one arrival per warp, mbarrier phase = panel): `full` completes when
   // every warp has stored its W/G entries of the next panel and its staged inputs have landed; `empty` when every
   // warp has issued its last DMMA of the panel.  A warp waits for `full` at the top of a panel and for the previous
-  // panel's `empty` only before its first store (a third of the way in), so the warps may drift apart by that much
+  // panel's `empty` only before its first store (a quarter of the way in), so the warps may drift apart by that much
   // instead of meeting at a CTA barrier every panel (the barrier was 9 % of all warp stall samples).
   const uint32_t bar_full = bar_base + 8u * LK_PSTAGES, bar_empty = bar_full + 8u;
   auto warp_arrive = [&](uint32_t bar) {
@@ -617,9 +617,8 @@ sample_likelihood_kernel(const LikelihoodSpectrum* __restrict__ specs) {
   // E col layout: pair (i,j) at i(i+1)/2 + j ; projection c_j at 216 + j.  Row 20 of the bordered factor is
   // z = L^-1 c, so quad = q - z'z (null_gp.py:345-358).  Thread t of a sample's group owns rows t, t + 8 and
   // t + 16 of the lower triangle (row 20 = the projection row) in three register arrays with compile-time
-  // indices; column j needs the finished entries of row j, which its owner broadcasts by shuffles, and every
-  // dot product is two independent FMA chains.  (The first version walked the matrix in shared memory with
-  // two loads per FMA and took 13 % of the kernel with the tensor pipe idle.)
+  // indices; the entries of a column that other threads need are broadcast by shuffles.  (The first version
+  // walked the matrix in shared memory with two loads per FMA and took 13 % of the kernel with the tensor pipe idle.)
   {
     const int s = tid >> 3;          // sample of this thread group (8 threads per sample)
     const int t = tid & 7;
@@ -641,45 +640,29 @@ sample_likelihood_kernel(const LikelihoodSpectrum* __restrict__ specs) {
       else if (i == LK_K) val = Es[(LK_PROJ_COL0 + k) * LK_EP_STRIDE];
       r2[k] = val;
     }
+    // Right-looking elimination: column j is scaled by 1/sqrt(pivot) and the trailing entries are updated at once,
+    // a_ik -= l_ij l_kj (j < k <= i).  The updates of a column are independent of each other, so the dependent
+    // chain per column is pivot broadcast -> rsqrt -> scale -> broadcast -> one FMA (the left-looking form, which
+    // collected a_ij - sum_k l_ik l_jk when it reached column j, had FMA chains of length j/2 in front of every
+    // pivot; this phase is latency-bound, it runs next to the other CTA's DMMAs).  Entries above the diagonal of a
+    // thread's rows are never read for a result; updating them costs nothing extra in SIMT.
     double piv_prod = 1.0;
 #pragma unroll
     for (int j = 0; j < LK_K; ++j) {
-      const int owner = gbase + (j & 7);
-      // finished entries of row j (k < j), from its owner
-      double Lj[LK_K];
-#pragma unroll
-      for (int k = 0; k < j; ++k)
-        Lj[k] = __shfl_sync(0xffffffffu, j < 8 ? r0[k < 8 ? k : 0] : j < 16 ? r1[k < 16 ? k : 0] : r2[k], owner);
-      // x_q = A[i_q][j] - sum_k L[i_q][k] L[j][k] for the rows of every slot that reaches column j
-      double x0 = 0.0, x1 = 0.0, x2 = r2[j];
-      if (j < 8) {
-        double e0 = r0[j], e1 = 0.0;
-#pragma unroll
-        for (int k = 0; k + 1 < j; k += 2) { e0 = fma(-r0[k], Lj[k], e0); e1 = fma(-r0[k + 1], Lj[k + 1], e1); }
-        if (j & 1) e0 = fma(-r0[j - 1], Lj[j - 1], e0);
-        x0 = e0 + e1;
-      }
-      if (j < 16) {
-        double e0 = r1[j], e1 = 0.0;
-#pragma unroll
-        for (int k = 0; k + 1 < j; k += 2) { e0 = fma(-r1[k], Lj[k], e0); e1 = fma(-r1[k + 1], Lj[k + 1], e1); }
-        if (j & 1) e0 = fma(-r1[j - 1], Lj[j - 1], e0);
-        x1 = e0 + e1;
-      }
-      {
-        double e0 = x2, e1 = 0.0;
-#pragma unroll
-        for (int k = 0; k + 1 < j; k += 2) { e0 = fma(-r2[k], Lj[k], e0); e1 = fma(-r2[k + 1], Lj[k + 1], e1); }
-        if (j & 1) e0 = fma(-r2[j - 1], Lj[j - 1], e0);
-        x2 = e0 + e1;
-      }
-      // the pivot is the x of row j itself
-      const double piv = __shfl_sync(0xffffffffu, j < 8 ? x0 : j < 16 ? x1 : x2, owner);
+      const double piv = __shfl_sync(0xffffffffu, j < 8 ? r0[j < 8 ? j : 0] : j < 16 ? r1[j < 16 ? j : 0] : r2[j], gbase + (j & 7));
       piv_prod *= piv;
       const double inv = fast_rsqrt(piv);
-      if (j < 8) r0[j] = x0 * inv;    // rows below j become column j of L (the pivot row's own entry is not used again)
-      if (j < 16) r1[j] = x1 * inv;
-      r2[j] = x2 * inv;
+      if (j < 8) r0[j < 8 ? j : 0] *= inv;  // rows below j: column j of L (row 20: z_j)
+      if (j < 16) r1[j < 16 ? j : 0] *= inv;
+      r2[j] *= inv;
+#pragma unroll
+      for (int k = j + 1; k < LK_K; ++k) {
+        // l_kj from the owner of row k
+        const double lkj = __shfl_sync(0xffffffffu, k < 8 ? r0[j < 8 ? j : 0] : k < 16 ? r1[j < 16 ? j : 0] : r2[j], gbase + (k & 7));
+        if (k < 8) r0[k < 8 ? k : 0] = fma(-r0[j < 8 ? j : 0], lkj, r0[k < 8 ? k : 0]);
+        if (k < 16) r1[k < 16 ? k : 0] = fma(-r1[j < 16 ? j : 0], lkj, r1[k < 16 ? k : 0]);
+        r2[k] = fma(-r2[j], lkj, r2[k]);
+      }
     }
     // z'z on the owner of row 20 (t = 4, third slot)
     if (t == 4 && tile_s0 + s < sp.num_samples) {
