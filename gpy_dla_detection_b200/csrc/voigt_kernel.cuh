@@ -181,10 +181,16 @@ voigt_profile_kernel(const AbsorptionGrid* __restrict__ grids, int num_lines, in
   const int nchunks = (g.n_in + 31) >> 5;
   double* ring = s_ring[warp][0];
   double* ring2 = s_ring[warp][1];
+  // the two global loads of an iteration are issued an iteration (wavelength) or a chunk of arithmetic (output
+  // index) ahead of their use (they were the kernel's only long-scoreboard stalls; with 8 resident warps per
+  // sub-partition the other warps covered most of them already: + 0.1 % of the step)
+  double lam_next = g.wl[min(lane, g.n_in - 1)];
   for (int j = 0; j <= nchunks; ++j) {
+    const int u = ((j - 1) << 5) + lane;     // output pixel of the convolution step of this iteration
+    const int q = (j >= 1 && u < n_u) ? g.qmap[u] : -1;
     if (j < nchunks) {
-      const int p = (j << 5) + lane;
-      const double lam = g.wl[min(p, g.n_in - 1)];                     // tail lanes: unused copies
+      const double lam = lam_next;                                      // tail lanes: unused copies
+      lam_next = g.wl[min(((j + 1) << 5) + lane, g.n_in - 1)];
       const double total = line_sum_at<NL>(lam, mult, num_lines);
       const double cube = lls ? lls_break_cube(lam, opz) : 0.0;        // warp-uniform branch
       const double rawv = profile_exp(__dsub_rn(__dmul_rn(nhi, total), __dmul_rn(lls_scale, cube)));
@@ -197,24 +203,18 @@ voigt_profile_kernel(const AbsorptionGrid* __restrict__ grids, int num_lines, in
       }
     }
     __syncwarp();
-    if (j >= 1) {
-      const int u = ((j - 1) << 5) + lane;
-      if (u < n_u) {
-        const int q = g.qmap[u];
-        if (q >= 0) {
-          const int w0 = (((j - 1) & 1) << 5) + lane;  // elements u .. u + 6
-          double acc = 0.0;
+    if (q >= 0) {
+      const int w0 = (((j - 1) & 1) << 5) + lane;  // elements u .. u + 6
+      double acc = 0.0;
 #pragma unroll
-          for (int k = 0; k <= 2 * INSTRUMENT_WIDTH; ++k) acc = fma(ring[w0 + k], c_instrument[2 * INSTRUMENT_WIDTH - k], acc);
-          out[q] = acc;
-          if (paired) {
-            double acc2 = 0.0;
+      for (int k = 0; k <= 2 * INSTRUMENT_WIDTH; ++k) acc = fma(ring[w0 + k], c_instrument[2 * INSTRUMENT_WIDTH - k], acc);
+      out[q] = acc;
+      if (paired) {
+        double acc2 = 0.0;
 #pragma unroll
-            for (int k = 0; k <= 2 * INSTRUMENT_WIDTH; ++k)
-              acc2 = fma(ring2[w0 + k], c_instrument[2 * INSTRUMENT_WIDTH - k], acc2);
-            out2[q] = acc2;
-          }
-        }
+        for (int k = 0; k <= 2 * INSTRUMENT_WIDTH; ++k)
+          acc2 = fma(ring2[w0 + k], c_instrument[2 * INSTRUMENT_WIDTH - k], acc2);
+        out2[q] = acc2;
       }
     }
     __syncwarp();  // chunk j-1 is overwritten by chunk j+1 in the next iteration
