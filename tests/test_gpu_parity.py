@@ -576,3 +576,26 @@ def test_likelihood_kernel_panel_tails_and_many_absorbers(gpu, O):
             assert np.all(np.isfinite(got)), (n_u, kd)
             worst = max(worst, H.ll_err(got, ref))
     assert worst < 1e-9, worst  # |d ll| / max(|ll|, 1), the tolerance of the full-size tests
+
+
+def test_catalogue_repeats_are_bit_identical(gpu):
+    """The likelihood kernel's warps run unsynchronised between split barriers: a lost phase or a race would show
+    as run-to-run differences.  Full-size samples (S = 10 000, max_dlas = 4), 24 spectra, 4 repeats; the long
+    version is tools/soak.py."""
+    from gpy_dla_detection_b200 import synthetic
+
+    st = H.Setup(10000)
+    z_qsos = synthetic.sample_z_qsos(24, seed=99)
+    spectra = [synthetic.make_spectrum(st.model, float(z), seed=500 + i) for i, z in enumerate(z_qsos)]
+    cat = st.catalogue(4, True, batch_spectra=16)
+    packed = cat.pack(spectra)
+    first = None
+    for _ in range(4):
+        out = cat.process(*packed, z_qsos, keep_samples=True)
+        arrays = {k: v for k, v in out.items() if isinstance(v, np.ndarray)}
+        if first is None:
+            first = {k: v.copy() for k, v in arrays.items()}
+            assert np.isfinite(first["p_dlas"]).all()
+            continue
+        for k, v in first.items():
+            assert np.array_equal(v, arrays[k], equal_nan=True), k
