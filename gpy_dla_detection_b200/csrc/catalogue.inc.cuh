@@ -61,43 +61,103 @@ __global__ void init_rows_kernel(int32_t* __restrict__ rows, int S, int nrows, c
 
 }  // namespace dla
 
+// ---------------------------------------------------------------------------------------------------
+// The engine is a two-deep software pipeline over batches of B spectra (tasks 5/6):
+//
+//   copy stream :  H2D(i+2) ...............                      (host source only; raw-input slot i & 1)
+//   main stream :  prep(i+1) | compute(i) | D2H(i) | prep(i+2) | compute(i+1) | D2H(i+1) | ...
+//   host        :  wait prep(i) -> size the batch, write descriptors -> enqueue compute(i) ->
+//                  consume results(i-1) -> enqueue H2D(i+2), prep(i+2)
+//
+// prepare_spectrum_kernel of batch i+1 is queued AHEAD of batch i's kernels, so the host has the pixel counts it
+// needs to size batch i+1 (profile cache, Gram basis, descriptors) long before batch i finishes: the device
+// never waits for the host between batches (round 1 synchronised twice per batch).  Everything the host hands
+// to or takes from an in-flight batch lives in page-locked staging owned by one of two slots (parity of the
+// batch index): descriptors, the prep scalars, the result block, the optional per-sample arrays.  The large
+// per-batch device workspace (profile cache, running product, basis, ...) is shared by all batches - their
+// kernels are serialised by the main stream.  Device memory holds at most two batches of raw spectra, so a
+// catalogue of any length streams through (the staged variant keeps the raw catalogue resident instead and
+// only measures the device path).
+// ---------------------------------------------------------------------------------------------------
+struct CatSlot {
+  // raw spectra of the batch (host source)
+  DevBuf<double> wl, flux, var;
+  DevBuf<uint8_t> mask;
+  // prepared arrays (written by prep(i), read by compute(i))
+  DevBuf<uint8_t> ind_unmasked, ind;
+  DevBuf<double> x, y, v, this_wl, mu, omega2, M, unmasked_wl, wl_abs, padded_wl, scratch, scalars;
+  DevBuf<int32_t> uidx;
+  DevBuf<PrepTask> prep_desc;
+  // page-locked host staging
+  PinnedBuf<PrepTask> h_prep;
+  PinnedBuf<double> h_scalars;          // [B][8]
+  PinnedBuf<unsigned char> h_desc;      // all descriptors of compute(i), one block
+  PinnedBuf<double> h_res;              // result block of the batch
+  PinnedBuf<int> h_alive;               // [B][4]
+  PinnedBuf<double> h_sample_dla, h_sample_sub;  // optional per-sample arrays
+  PinnedBuf<int32_t> h_inds;
+  // bookkeeping of the batch in flight
+  int q0 = 0, nb = 0;
+  std::vector<int> n_b;
+  std::vector<double> zmin_b, zmax_b;
+  cudaEvent_t ev_upload = nullptr, ev_prep = nullptr, ev_done = nullptr, ev_v0 = nullptr, ev_v1 = nullptr;
+  cudaEvent_t ev_lk[2 * LK_MAX_ROWS] = {nullptr};
+  bool prep_recorded = false;
+  ~CatSlot() {
+    for (cudaEvent_t e : {ev_upload, ev_prep, ev_done, ev_v0, ev_v1})
+      if (e) cudaEventDestroy(e);
+    for (cudaEvent_t e : ev_lk)
+      if (e) cudaEventDestroy(e);
+  }
+};
+
 struct dla_catalogue {
   const dla_model* model = nullptr;
   dla_params params;
+  int device = -1;
   int S = 0, max_dlas = 0, B = 0, keep = 0;
   bool paired_offsets = false;  // DLA and subDLA samples share their redshift offsets: one line-sum evaluation for both
   // constants
   DevBuf<double> dla_offsets, dla_log_nhi, sub_offsets, nhi_all /* [dla_nhi ; sub_nhi] */, uniforms;
-  // staged inputs
+  // staged inputs (dla_catalogue_stage)
   int Q = 0;
   std::vector<int64_t> pix_off;
   std::vector<double> z_qsos;
   DevBuf<double> wl, flux, var, log_priors_in;
   DevBuf<uint8_t> mask;
   int max_n_raw = 0;
-  // per-batch workspace
-  DevBuf<uint8_t> ind_unmasked, ind;
-  DevBuf<double> x, y, v, this_wl, mu, omega2, M, unmasked_wl, wl_abs, padded_wl, scratch, scalars;
-  DevBuf<int32_t> uidx, qmap;
+  DevBuf<double> log_priors_call;  // priors of a dla_catalogue_process call
+  // the two pipeline slots
+  CatSlot slot[2];
+  // per-batch compute workspace, shared by all batches (stream-ordered)
+  DevBuf<int32_t> qmap;
   DevBuf<double> z_samples, cache, prod, raw_ll0, raw_ll, sample_ll_dla, sample_ll_sub, log_ev_dla, log_ev_sub, cdf;
-  DevBuf<double> log_lik, log_priors, log_post, model_post, p_dla, p_no_dla, map_z, map_lognhi;
+  DevBuf<double> res;    // [log_priors | log_lik | log_post | model_post] (B x m each), p_dla, p_no_dla (B), map_z, map_lognhi (B x md x md)
   DevBuf<double> basis;  // Gram basis panels of the batch's spectra
-  DevBuf<GramBasisTask> basis_desc;
   DevBuf<int32_t> rows, inds_t, map_ind;
   DevBuf<int> alive;  // [B][4] : DLA level-loop alive flag, status, usable (constant), pad
-  DevBuf<PrepTask> prep_desc;
-  DevBuf<AbsorptionGrid> grid_desc;
-  DevBuf<LikelihoodSpectrum> lk_desc;
-  DevBuf<EvidenceLevel> ev_desc;
-  DevBuf<MapTask> map_desc;
-  DevBuf<GatherTask> gather_desc;
-  std::vector<cudaEvent_t> events;
+  DevBuf<unsigned char> desc;  // device copy of the descriptor block
+  cudaEvent_t ev_call0 = nullptr, ev_call1 = nullptr;
   // timing of the last run
   double total_ms = 0, gram_ms = 0, voigt_ms = 0, gram_flops = 0;
   long long launches = 0;
   ~dla_catalogue() {
-    for (cudaEvent_t e : events) cudaEventDestroy(e);
+    if (ev_call0) cudaEventDestroy(ev_call0);
+    if (ev_call1) cudaEventDestroy(ev_call1);
   }
+};
+
+// where the raw spectra of a run come from
+struct CatSource {
+  bool on_device;            // staged: pointers are device arrays of the whole catalogue
+  const int64_t* pix_off;    // Q + 1
+  const double* wl;
+  const double* flux;
+  const double* var;
+  const uint8_t* mask;
+  const double* z_qsos;
+  int Q;
+  int max_n_raw;
 };
 
 extern "C" int dla_catalogue_create(const dla_model* model, const dla_params* params, const dla_catalogue_config* config,
@@ -115,9 +175,11 @@ extern "C" int dla_catalogue_create(const dla_model* model, const dla_params* pa
   DLA_REQUIRE(model->dev.k == LK_K, "the batched likelihood path is built for k = 20");
   DLA_REQUIRE(params->width == INSTRUMENT_WIDTH, "instrument profile width must be 3");
   DLA_REQUIRE(params->num_lines >= 1 && params->num_lines <= LYMAN_NUM_LINES, "num_lines must be in [1, 31]");
+  DLA_REQUIRE(model->device == rt.device, "the model lives on another device than the one selected by dla_init");
   std::unique_ptr<dla_catalogue> cat(new dla_catalogue());
   cat->model = model;
   cat->params = *params;
+  cat->device = rt.device;
   cat->S = S;
   cat->max_dlas = max_dlas;
   cat->B = config->batch_spectra > 0 ? config->batch_spectra : 64;
@@ -136,13 +198,41 @@ extern "C" int dla_catalogue_create(const dla_model* model, const dla_params* pa
     DLA_CUDA(cat->uniforms.alloc((size_t)(max_dlas - 1) * S));
     DLA_CUDA(cat->uniforms.upload(uniforms, (size_t)(max_dlas - 1) * S, rt.stream));
   }
+  DLA_CUDA(cudaEventCreate(&cat->ev_call0));
+  DLA_CUDA(cudaEventCreate(&cat->ev_call1));
+  for (CatSlot& sl : cat->slot) {
+    DLA_CUDA(cudaEventCreateWithFlags(&sl.ev_upload, cudaEventDisableTiming));
+    DLA_CUDA(cudaEventCreateWithFlags(&sl.ev_prep, cudaEventDisableTiming));
+    DLA_CUDA(cudaEventCreateWithFlags(&sl.ev_done, cudaEventDisableTiming));
+    DLA_CUDA(cudaEventCreate(&sl.ev_v0));
+    DLA_CUDA(cudaEventCreate(&sl.ev_v1));
+    for (int i = 0; i < 2 * max_dlas; ++i) DLA_CUDA(cudaEventCreate(&sl.ev_lk[i]));
+  }
   DLA_CUDA(cudaStreamSynchronize(rt.stream));
   *out = cat.release();
   return 0;
 }
 
 extern "C" int dla_catalogue_destroy(dla_catalogue* cat) {
+  if (cat) {
+    cudaStreamSynchronize(runtime().stream);
+    cudaStreamSynchronize(runtime().copy_stream);
+  }
   delete cat;
+  return 0;
+}
+
+static int cat_check_offsets(int num_spectra, const int64_t* pixel_offsets, int* max_n_raw) {
+  DLA_REQUIRE(num_spectra >= 1, "empty catalogue");
+  const int64_t total = pixel_offsets[num_spectra];
+  DLA_REQUIRE(pixel_offsets[0] == 0 && total >= 1, "pixel_offsets must start at 0");
+  int mx = 0;
+  for (int q = 0; q < num_spectra; ++q) {
+    const int64_t nr = pixel_offsets[q + 1] - pixel_offsets[q];
+    DLA_REQUIRE(nr >= 1 && nr < (1 << 30), "bad pixel_offsets");
+    mx = std::max(mx, (int)nr);
+  }
+  *max_n_raw = mx;
   return 0;
 }
 
@@ -153,18 +243,13 @@ extern "C" int dla_catalogue_stage(dla_catalogue* cat, int num_spectra, const in
   Runtime& rt = runtime();
   DLA_REQUIRE(cat && pixel_offsets && wavelengths && flux && noise_variance && pixel_mask && z_qsos && log_priors_in,
               "null pointer argument");
-  DLA_REQUIRE(num_spectra >= 1, "empty catalogue");
+  DLA_REQUIRE(cat->device == rt.device, "the catalogue lives on another device than the one selected by dla_init");
+  int max_n_raw = 0;
+  if (int rc = cat_check_offsets(num_spectra, pixel_offsets, &max_n_raw)) return rc;
   const int64_t total = pixel_offsets[num_spectra];
-  DLA_REQUIRE(pixel_offsets[0] == 0 && total >= 1, "pixel_offsets must start at 0");
   cat->Q = num_spectra;
   cat->pix_off.assign(pixel_offsets, pixel_offsets + num_spectra + 1);
   cat->z_qsos.assign(z_qsos, z_qsos + num_spectra);
-  int max_n_raw = 0;
-  for (int q = 0; q < num_spectra; ++q) {
-    const int64_t nr = pixel_offsets[q + 1] - pixel_offsets[q];
-    DLA_REQUIRE(nr >= 1 && nr < (1 << 30), "bad pixel_offsets");
-    max_n_raw = std::max(max_n_raw, (int)nr);
-  }
   cat->max_n_raw = max_n_raw;
   const int m = 2 + cat->max_dlas;
   DLA_CUDA(cat->wl.ensure(total));
@@ -181,34 +266,79 @@ extern "C" int dla_catalogue_stage(dla_catalogue* cat, int num_spectra, const in
   return 0;
 }
 
-static cudaEvent_t cat_event(dla_catalogue* cat, size_t i) {
-  while (cat->events.size() <= i) {
-    cudaEvent_t e;
-    cudaEventCreate(&e);
-    cat->events.push_back(e);
-  }
-  return cat->events[i];
+// layout of the device result block for a batch capacity of B spectra (offsets in doubles)
+struct CatResLayout {
+  size_t log_priors, log_lik, log_post, model_post, p_dla, p_no_dla, map_z, map_lognhi, total;
+};
+static CatResLayout cat_res_layout(size_t B, size_t m, size_t md) {
+  CatResLayout L;
+  size_t o = 0;
+  L.log_priors = o; o += B * m;
+  L.log_lik = o; o += B * m;
+  L.log_post = o; o += B * m;
+  L.model_post = o; o += B * m;
+  L.p_dla = o; o += B;
+  L.p_no_dla = o; o += B;
+  L.map_z = o; o += B * md * md;
+  L.map_lognhi = o; o += B * md * md;
+  L.total = o;
+  return L;
 }
 
-static int cat_ensure_workspace(dla_catalogue* cat) {
-  const size_t B = cat->B, cap = cat->max_n_raw, S = cat->S, md = cat->max_dlas, m = 2 + md;
+// descriptor block of one batch: byte offsets of the typed arrays inside it
+struct CatDescLayout {
+  size_t basis, grid, lk, ev, map, gather, total;
+};
+static CatDescLayout cat_desc_layout(size_t B, size_t md) {
+  auto up = [](size_t x) { return (x + 255) / 256 * 256; };
+  CatDescLayout L;
+  size_t o = 0;
+  L.basis = o; o = up(o + sizeof(GramBasisTask) * B);
+  L.grid = o; o = up(o + sizeof(AbsorptionGrid) * B);
+  L.lk = o; o = up(o + sizeof(LikelihoodSpectrum) * B * md);
+  L.ev = o; o = up(o + sizeof(EvidenceLevel) * B * (md + 1));
+  L.map = o; o = up(o + sizeof(MapTask) * B);
+  L.gather = o; o = up(o + sizeof(GatherTask) * B);
+  L.total = o;
+  return L;
+}
+
+static int cat_ensure_workspace(dla_catalogue* cat, size_t cap, bool host_source, const dla_catalogue_outputs* o) {
+  const size_t B = cat->B, S = cat->S, md = cat->max_dlas, m = 2 + md;
   const size_t w = cat->params.width;
-  DLA_CUDA(cat->ind_unmasked.ensure(B * cap));
-  DLA_CUDA(cat->ind.ensure(B * cap));
-  DLA_CUDA(cat->x.ensure(B * cap));
-  DLA_CUDA(cat->y.ensure(B * cap));
-  DLA_CUDA(cat->v.ensure(B * cap));
-  DLA_CUDA(cat->this_wl.ensure(B * cap));
-  DLA_CUDA(cat->mu.ensure(B * cap));
-  DLA_CUDA(cat->omega2.ensure(B * cap));
-  DLA_CUDA(cat->M.ensure(B * cap * LK_K));
-  DLA_CUDA(cat->uidx.ensure(B * cap));
+  for (CatSlot& sl : cat->slot) {
+    if (host_source) {
+      DLA_CUDA(sl.wl.ensure(B * cap));
+      DLA_CUDA(sl.flux.ensure(B * cap));
+      DLA_CUDA(sl.var.ensure(B * cap));
+      DLA_CUDA(sl.mask.ensure(B * cap));
+    }
+    DLA_CUDA(sl.ind_unmasked.ensure(B * cap));
+    DLA_CUDA(sl.ind.ensure(B * cap));
+    DLA_CUDA(sl.x.ensure(B * cap));
+    DLA_CUDA(sl.y.ensure(B * cap));
+    DLA_CUDA(sl.v.ensure(B * cap));
+    DLA_CUDA(sl.this_wl.ensure(B * cap));
+    DLA_CUDA(sl.mu.ensure(B * cap));
+    DLA_CUDA(sl.omega2.ensure(B * cap));
+    DLA_CUDA(sl.M.ensure(B * cap * LK_K));
+    DLA_CUDA(sl.uidx.ensure(B * cap));
+    DLA_CUDA(sl.unmasked_wl.ensure(B * cap));
+    DLA_CUDA(sl.wl_abs.ensure(B * (cap + 2 * w)));
+    DLA_CUDA(sl.padded_wl.ensure(B * (cap + 2 * w)));
+    DLA_CUDA(sl.scratch.ensure(B * cap));
+    DLA_CUDA(sl.scalars.ensure(B * 8));
+    DLA_CUDA(sl.prep_desc.ensure(B));
+    DLA_CUDA(sl.h_prep.ensure(B));
+    DLA_CUDA(sl.h_scalars.ensure(B * 8));
+    DLA_CUDA(sl.h_desc.ensure(cat_desc_layout(B, md).total));
+    DLA_CUDA(sl.h_res.ensure(cat_res_layout(B, m, md).total));
+    DLA_CUDA(sl.h_alive.ensure(B * 4));
+    if (o->sample_log_likelihoods_dla) DLA_CUDA(sl.h_sample_dla.ensure(B * S * md));
+    if (o->sample_log_likelihoods_lls) DLA_CUDA(sl.h_sample_sub.ensure(B * S));
+    if (o->base_sample_inds && md > 1) DLA_CUDA(sl.h_inds.ensure(B * S * (md - 1)));
+  }
   DLA_CUDA(cat->qmap.ensure(B * cap));
-  DLA_CUDA(cat->unmasked_wl.ensure(B * cap));
-  DLA_CUDA(cat->wl_abs.ensure(B * (cap + 2 * w)));
-  DLA_CUDA(cat->padded_wl.ensure(B * (cap + 2 * w)));
-  DLA_CUDA(cat->scratch.ensure(B * cap));
-  DLA_CUDA(cat->scalars.ensure(B * 8));
   DLA_CUDA(cat->z_samples.ensure(B * 2 * S));
   DLA_CUDA(cat->raw_ll0.ensure(B * (2 * S + 1)));
   DLA_CUDA(cat->raw_ll.ensure(B * S));
@@ -221,368 +351,419 @@ static int cat_ensure_workspace(dla_catalogue* cat) {
   DLA_CUDA(cat->inds_t.ensure(B * S * std::max<size_t>(md - 1, 1)));
   DLA_CUDA(cat->map_ind.ensure(B * md));
   DLA_CUDA(cat->alive.ensure(B * 4));
-  DLA_CUDA(cat->log_lik.ensure(B * m));
-  DLA_CUDA(cat->log_priors.ensure(B * m));
-  DLA_CUDA(cat->log_post.ensure(B * m));
-  DLA_CUDA(cat->model_post.ensure(B * m));
-  DLA_CUDA(cat->p_dla.ensure(B));
-  DLA_CUDA(cat->p_no_dla.ensure(B));
-  DLA_CUDA(cat->map_z.ensure(B * md * md));
-  DLA_CUDA(cat->map_lognhi.ensure(B * md * md));
-  DLA_CUDA(cat->prep_desc.ensure(B));
-  DLA_CUDA(cat->grid_desc.ensure(B));
-  DLA_CUDA(cat->lk_desc.ensure(B * md));
-  DLA_CUDA(cat->ev_desc.ensure(B * (md + 1)));
-  DLA_CUDA(cat->map_desc.ensure(B));
-  DLA_CUDA(cat->gather_desc.ensure(B));
+  DLA_CUDA(cat->res.ensure(cat_res_layout(B, m, md).total));
+  DLA_CUDA(cat->desc.ensure(cat_desc_layout(B, md).total));
   return 0;
 }
 
-extern "C" int dla_catalogue_run_staged(dla_catalogue* cat, dla_catalogue_outputs* o) {
-  DLA_CHECK_READY();
+// ---- pipeline stage: raw spectra of batch `bi` -> device slot (host source), on the copy stream ---------------
+static int cat_enqueue_upload(dla_catalogue* cat, const CatSource& src, int bi) {
   Runtime& rt = runtime();
-  DLA_REQUIRE(cat && o, "null pointer argument");
-  DLA_REQUIRE(cat->Q >= 1, "nothing staged");
+  CatSlot& sl = cat->slot[bi & 1];
+  const int q0 = bi * cat->B, nb = std::min(cat->B, src.Q - q0);
+  const int64_t a = src.pix_off[q0], total = src.pix_off[q0 + nb] - a;
+  // the slot's raw buffers were last read by prep(bi - 2)
+  if (sl.prep_recorded) DLA_CUDA(cudaStreamWaitEvent(rt.copy_stream, sl.ev_prep, 0));
+  DLA_CUDA(cudaMemcpyAsync(sl.wl.p, src.wl + a, sizeof(double) * total, cudaMemcpyHostToDevice, rt.copy_stream));
+  DLA_CUDA(cudaMemcpyAsync(sl.flux.p, src.flux + a, sizeof(double) * total, cudaMemcpyHostToDevice, rt.copy_stream));
+  DLA_CUDA(cudaMemcpyAsync(sl.var.p, src.var + a, sizeof(double) * total, cudaMemcpyHostToDevice, rt.copy_stream));
+  DLA_CUDA(cudaMemcpyAsync(sl.mask.p, src.mask + a, total, cudaMemcpyHostToDevice, rt.copy_stream));
+  DLA_CUDA(cudaEventRecord(sl.ev_upload, rt.copy_stream));
+  return 0;
+}
+
+// ---- pipeline stage: prepare_spectrum_kernel of batch `bi` + read-back of its scalars --------------------------
+static int cat_enqueue_prep(dla_catalogue* cat, const CatSource& src, int bi, const PrepParams& P, size_t cap) {
+  Runtime& rt = runtime();
+  CatSlot& sl = cat->slot[bi & 1];
+  const int w = cat->params.width;
+  const int q0 = bi * cat->B, nb = std::min(cat->B, src.Q - q0);
+  sl.q0 = q0;
+  sl.nb = nb;
+  const int64_t base = src.pix_off[q0];
+  for (int b = 0; b < nb; ++b) {
+    const int64_t off = src.pix_off[q0 + b];
+    PrepTask t;
+    t.X = nullptr;
+    if (src.on_device) {
+      t.Wobs = src.wl + off;
+      t.Y = src.flux + off;
+      t.V = src.var + off;
+      t.mask = src.mask + off;
+    } else {
+      t.Wobs = sl.wl.p + (off - base);
+      t.Y = sl.flux.p + (off - base);
+      t.V = sl.var.p + (off - base);
+      t.mask = sl.mask.p + (off - base);
+    }
+    t.n_raw = (int)(src.pix_off[q0 + b + 1] - off);
+    t.z_qso = src.z_qsos[q0 + b];
+    t.ind_unmasked = sl.ind_unmasked.p + b * cap;
+    t.ind = sl.ind.p + b * cap;
+    t.x = sl.x.p + b * cap;
+    t.y = sl.y.p + b * cap;
+    t.v = sl.v.p + b * cap;
+    t.this_wl = sl.this_wl.p + b * cap;
+    t.mu = sl.mu.p + b * cap;
+    t.omega2 = sl.omega2.p + b * cap;
+    t.M = sl.M.p + b * cap * LK_K;
+    t.uidx = sl.uidx.p + b * cap;
+    t.unmasked_wl = sl.unmasked_wl.p + b * cap;
+    t.wl_abs = sl.wl_abs.p + b * (cap + 2 * w);
+    t.padded_wl = sl.padded_wl.p + b * (cap + 2 * w);
+    t.scratch = sl.scratch.p + b * cap;
+    t.scalars = sl.scalars.p + (size_t)b * 8;
+    sl.h_prep.p[b] = t;
+  }
+  if (!src.on_device) DLA_CUDA(cudaStreamWaitEvent(rt.stream, sl.ev_upload, 0));
+  DLA_CUDA(cudaMemcpyAsync(sl.prep_desc.p, sl.h_prep.p, sizeof(PrepTask) * nb, cudaMemcpyHostToDevice, rt.stream));
+  prepare_spectrum_kernel<<<nb, 256, 0, rt.stream>>>(sl.prep_desc.p, cat->model->dev, P);
+  DLA_LAUNCHED();
+  DLA_CUDA(cudaMemcpyAsync(sl.h_scalars.p, sl.scalars.p, sizeof(double) * nb * 8, cudaMemcpyDeviceToHost, rt.stream));
+  DLA_CUDA(cudaEventRecord(sl.ev_prep, rt.stream));
+  sl.prep_recorded = true;
+  return 0;
+}
+
+// ---- pipeline stage: size batch `bi`, write its descriptors, enqueue every kernel and the result read-back ------
+static int cat_enqueue_compute(dla_catalogue* cat, int bi, size_t cap, const dla_catalogue_outputs* o,
+                               const double* d_log_priors_in) {
+  Runtime& rt = runtime();
+  CatSlot& sl = cat->slot[bi & 1];
   const int S = cat->S, md = cat->max_dlas, m = 2 + md, w = cat->params.width;
-  const size_t cap = cat->max_n_raw;
+  const int nb = sl.nb, q0 = sl.q0;
+  const size_t B = cat->B;
   const double nan = std::numeric_limits<double>::quiet_NaN();
-  int rc = cat_ensure_workspace(cat);
+  int rc = 0;
+  DLA_CUDA(cudaEventSynchronize(sl.ev_prep));  // long done: prep(bi) was queued ahead of compute(bi - 1)
+  const double* h_scalars = sl.h_scalars.p;
+
+  // ---- sizes, cache layout --------------------------------------------------------------------
+  sl.n_b.resize(nb);
+  sl.zmin_b.resize(nb);
+  sl.zmax_b.resize(nb);
+  std::vector<int> nu_b(nb), ld_b(nb);
+  std::vector<size_t> cache_off(nb), prod_off(nb), basis_off(nb);
+  size_t cache_total = 0, prod_total = 0, basis_total = 0;
+  int max_basis_rows = LK_KC, max_ld = 1;
+  for (int b = 0; b < nb; ++b) {
+    nu_b[b] = (int)h_scalars[(size_t)b * 8 + 0];
+    sl.n_b[b] = (int)h_scalars[(size_t)b * 8 + 1];
+    sl.zmin_b[b] = h_scalars[(size_t)b * 8 + 5];
+    sl.zmax_b[b] = h_scalars[(size_t)b * 8 + 6];
+    ld_b[b] = (int)round_up(std::max(sl.n_b[b], 1), 4);
+    max_ld = std::max(max_ld, ld_b[b]);
+    cache_off[b] = cache_total;
+    cache_total += (size_t)(2 * S + 1) * ld_b[b];
+    prod_off[b] = prod_total;
+    if (md >= 3) prod_total += (size_t)S * ld_b[b];
+    const size_t brows = round_up((size_t)std::max(sl.n_b[b], 1), LK_KC);
+    basis_off[b] = basis_total;
+    basis_total += brows * LK_PSTRIDE;
+    max_basis_rows = std::max(max_basis_rows, (int)brows);
+  }
+  // grown with head-room: a re-allocation frees memory the previous batch may still be using, which CUDA
+  // resolves by synchronising the device - correct, but a pipeline bubble
+  if (cache_total > cat->cache.n) DLA_CUDA(cat->cache.ensure(cache_total + cache_total / 8));
+  if (prod_total > cat->prod.n) DLA_CUDA(cat->prod.ensure(prod_total + prod_total / 8));
+  if (basis_total > cat->basis.n) DLA_CUDA(cat->basis.ensure(basis_total + basis_total / 8));
+
+  // ---- descriptors, written straight into the slot's page-locked block ---------------------------------
+  const CatDescLayout DL = cat_desc_layout(B, md);
+  const CatResLayout RL = cat_res_layout(B, m, md);
+  unsigned char* hd = sl.h_desc.p;
+  GramBasisTask* h_basis = reinterpret_cast<GramBasisTask*>(hd + DL.basis);
+  AbsorptionGrid* h_grid = reinterpret_cast<AbsorptionGrid*>(hd + DL.grid);
+  LikelihoodSpectrum* h_lk = reinterpret_cast<LikelihoodSpectrum*>(hd + DL.lk);
+  EvidenceLevel* h_ev = reinterpret_cast<EvidenceLevel*>(hd + DL.ev);
+  MapTask* h_map = reinterpret_cast<MapTask*>(hd + DL.map);
+  GatherTask* h_gather = reinterpret_cast<GatherTask*>(hd + DL.gather);
+  const GramBasisTask* d_basis = reinterpret_cast<const GramBasisTask*>(cat->desc.p + DL.basis);
+  const AbsorptionGrid* d_grid = reinterpret_cast<const AbsorptionGrid*>(cat->desc.p + DL.grid);
+  const LikelihoodSpectrum* d_lk = reinterpret_cast<const LikelihoodSpectrum*>(cat->desc.p + DL.lk);
+  const EvidenceLevel* d_ev = reinterpret_cast<const EvidenceLevel*>(cat->desc.p + DL.ev);
+  const MapTask* d_map = reinterpret_cast<const MapTask*>(cat->desc.p + DL.map);
+  const GatherTask* d_gather = reinterpret_cast<const GatherTask*>(cat->desc.p + DL.gather);
+  int* h_alive = sl.h_alive.p;
+  double* res = cat->res.p;
+  for (int b = 0; b < nb; ++b) {
+    const PrepTask& pt = sl.h_prep.p[b];
+    const int n = sl.n_b[b];
+    const bool usable = n >= 1 && isfinite(h_scalars[(size_t)b * 8 + 3]) && isfinite(h_scalars[(size_t)b * 8 + 4]);
+    h_alive[(size_t)b * 4 + 0] = usable ? 1 : 0;
+    h_alive[(size_t)b * 4 + 1] = usable ? 0 : 1;  // status 1: nothing to model
+    h_alive[(size_t)b * 4 + 2] = usable ? 1 : 0;
+    h_alive[(size_t)b * 4 + 3] = 0;
+    double* cache_b = cat->cache.p + cache_off[b];
+    h_basis[b].M = pt.M;
+    h_basis[b].P = cat->basis.p + basis_off[b];
+    h_basis[b].n = n;
+    AbsorptionGrid g;
+    g.wl = pt.wl_abs;
+    g.uidx = pt.uidx;
+    g.qmap = cat->qmap.p + (size_t)b * cap;
+    g.out = cache_b;
+    g.n_in = cat->params.broadening ? nu_b[b] + 2 * w : nu_b[b];
+    g.n_out = n;
+    g.ld = ld_b[b];
+    g.num_samples = usable ? 2 * S : 0;
+    g.z = cat->z_samples.p + (size_t)b * 2 * S;
+    g.nhi = cat->nhi_all.p;
+    g.pair_offset = cat->paired_offsets ? S : 0;
+    g.lls_break = 0;
+    h_grid[b] = g;
+    for (int level = 0; level < md; ++level) {
+      LikelihoodSpectrum d;
+      d.y = pt.y;
+      d.v = pt.v;
+      d.mu = pt.mu;
+      d.omega2 = pt.omega2;
+      d.M = pt.M;
+      d.P = cat->basis.p + basis_off[b];
+      d.cache = cache_b;
+      d.rows0 = nullptr;
+      d.alive = cat->alive.p + (size_t)b * 4;
+      d.n = n;
+      d.ld = ld_b[b];
+      d.row0 = 0;
+      if (level == 0) {  // DLA + subDLA + null rows in one go
+        d.base0 = cache_b;
+        d.rows = nullptr;
+        d.prod_out = nullptr;
+        d.out = cat->raw_ll0.p + (size_t)b * (2 * S + 1);
+        d.num_samples = 2 * S + 1;
+        d.num_rows = 1;
+        d.row_stride = 0;
+      } else {
+        // Running product of the previous level (row s) x profile of the newly drawn absorber.
+        // In-place update at levels >= 2 (prod_out == base0): element (s, p) of the product buffer is read and
+        // written by exactly ONE thread of ONE CTA - the thread that owns pixel p of sample s in the tile that
+        // owns sample s - and that thread's store (scalar slot 0 of the panel's chain, after its cp.async of
+        // the same element has been waited for through the `full` barrier) is program-ordered after its own
+        // read of the staged copy.  No other CTA touches row s: factor 0 of sample s' is row s' of the
+        // buffer, never row s.  (Factor >= 1 rows come from the read-only profile cache.)
+        double* prod_b = cat->prod.p + prod_off[b];
+        d.base0 = level == 1 ? cache_b : prod_b;
+        d.rows = cat->rows.p + (size_t)b * S * md + (size_t)level * S;
+        d.prod_out = (level + 1 < md) ? prod_b : nullptr;
+        d.out = cat->raw_ll.p + (size_t)b * S;
+        d.num_samples = S;
+        d.num_rows = 2;
+        d.row_stride = S;
+      }
+      h_lk[(size_t)level * nb + b] = d;
+      EvidenceLevel e;
+      e.raw_ll = level == 0 ? cat->raw_ll0.p + (size_t)b * (2 * S + 1) : cat->raw_ll.p + (size_t)b * S;
+      e.sample_ll = cat->sample_ll_dla.p + (size_t)b * S * md + level;
+      e.ll_stride = md;
+      e.z_samples = cat->z_samples.p + (size_t)b * 2 * S;
+      e.base_inds = cat->rows.p + (size_t)b * S * md + S;
+      e.base_out = (level + 1 < md) ? cat->rows.p + (size_t)b * S * md + (size_t)(level + 1) * S : nullptr;
+      e.uniforms = (level + 1 < md) ? cat->uniforms.p + (size_t)level * S : nullptr;
+      e.log_evidence = cat->log_ev_dla.p + (size_t)b * md + level;
+      e.cdf_scratch = cat->cdf.p + (size_t)b * S;
+      e.alive = cat->alive.p + (size_t)b * 4;
+      e.status = cat->alive.p + (size_t)b * 4 + 1;
+      e.S = S;
+      e.level = level;
+      e.min_z_separation = cat->params.min_z_separation;
+      h_ev[(size_t)level * nb + b] = e;
+    }
+    {  // subDLA model: one level, no resampling (subdla_gp.py, max_dlas = 1)
+      EvidenceLevel e;
+      e.raw_ll = cat->raw_ll0.p + (size_t)b * (2 * S + 1) + S;
+      e.sample_ll = cat->sample_ll_sub.p + (size_t)b * S;
+      e.ll_stride = 1;
+      e.z_samples = cat->z_samples.p + (size_t)b * 2 * S + S;
+      e.base_inds = nullptr;
+      e.base_out = nullptr;
+      e.uniforms = nullptr;
+      e.log_evidence = cat->log_ev_sub.p + b;
+      e.cdf_scratch = nullptr;
+      e.alive = cat->alive.p + (size_t)b * 4 + 2;  // not affected by the DLA model's early exit
+      e.status = nullptr;
+      e.S = S;
+      e.level = 0;
+      e.min_z_separation = cat->params.min_z_separation;
+      h_ev[(size_t)md * nb + b] = e;
+    }
+    MapTask mt;
+    mt.sample_ll = cat->sample_ll_dla.p + (size_t)b * S * md;
+    mt.base_inds = cat->rows.p + (size_t)b * S * md + S;
+    mt.z_samples = cat->z_samples.p + (size_t)b * 2 * S;
+    mt.log_nhi = cat->dla_log_nhi.p;
+    mt.map_z = res + RL.map_z + (size_t)b * md * md;
+    mt.map_log_nhi = res + RL.map_lognhi + (size_t)b * md * md;
+    mt.map_ind = cat->map_ind.p + (size_t)b * md;
+    mt.S = S;
+    mt.max_dlas = md;
+    h_map[b] = mt;
+    GatherTask gt;
+    gt.raw_ll0 = cat->raw_ll0.p + (size_t)b * (2 * S + 1);
+    gt.log_ev_dla = cat->log_ev_dla.p + (size_t)b * md;
+    gt.log_ev_sub = cat->log_ev_sub.p + b;
+    gt.log_lik = res + RL.log_lik + (size_t)b * m;
+    gt.S = S;
+    gt.max_dlas = md;
+    h_gather[b] = gt;
+  }
+  DLA_CUDA(cudaMemcpyAsync(cat->desc.p, hd, DL.total, cudaMemcpyHostToDevice, rt.stream));
+  DLA_CUDA(cudaMemcpyAsync(cat->alive.p, h_alive, sizeof(int) * nb * 4, cudaMemcpyHostToDevice, rt.stream));
+
+  // ---- launches ------------------------------------------------------------------------------
+  auto fill = [&](double* p, size_t count, double value) -> int {
+    fill_double_kernel<<<(unsigned)((count + 255) / 256), 256, 0, rt.stream>>>(p, count, value);
+    DLA_LAUNCHED();
+    return 0;
+  };
+  if ((rc = fill(cat->sample_ll_dla.p, (size_t)nb * S * md, nan))) return rc;
+  if ((rc = fill(cat->sample_ll_sub.p, (size_t)nb * S, nan))) return rc;
+  if ((rc = fill(cat->log_ev_dla.p, (size_t)nb * md, nan))) return rc;
+  if ((rc = fill(cat->log_ev_sub.p, (size_t)nb, nan))) return rc;
+  if ((rc = fill(cat->raw_ll0.p, (size_t)nb * (2 * S + 1), nan))) return rc;
+  {
+    const size_t work = std::max((size_t)S * md, (size_t)max_ld);
+    dim3 grid((unsigned)((work + 255) / 256), nb);
+    init_rows_kernel<<<grid, 256, 0, rt.stream>>>(cat->rows.p, S, md, d_grid);
+    DLA_LAUNCHED();
+  }
+  gram_basis_kernel<<<dim3((unsigned)((max_basis_rows + 7) / 8), nb), 256, 0, rt.stream>>>(d_basis);
+  DLA_LAUNCHED();
+  {
+    dim3 grid((2 * S + 255) / 256, nb);
+    z_samples_kernel<<<grid, 256, 0, rt.stream>>>(sl.scalars.p, 8, cat->dla_offsets.p, cat->sub_offsets.p, S, cat->z_samples.p);
+    DLA_LAUNCHED();
+  }
+  build_qmap_kernel<<<nb, 256, 0, rt.stream>>>(d_grid, cat->params.broadening);
+  DLA_LAUNCHED();
+  DLA_CUDA(cudaEventRecord(sl.ev_v0, rt.stream));
+  if ((rc = launch_voigt_grids(d_grid, cat->paired_offsets ? S : 2 * S, nb, cat->params.num_lines, cat->params.broadening)))
+    return rc;
+  DLA_CUDA(cudaEventRecord(sl.ev_v1, rt.stream));
+  for (int level = 0; level < md; ++level) {
+    DLA_CUDA(cudaEventRecord(sl.ev_lk[2 * level], rt.stream));
+    const int ns = level == 0 ? 2 * S + 1 : S;
+    dim3 grid((ns + LK_TS - 1) / LK_TS, nb);
+    sample_likelihood_kernel<<<grid, LK_THREADS, LK_SMEM_BYTES, rt.stream>>>(d_lk + (size_t)level * nb);
+    DLA_LAUNCHED();
+    DLA_CUDA(cudaEventRecord(sl.ev_lk[2 * level + 1], rt.stream));
+    evidence_level_kernel<<<nb, 1024, 0, rt.stream>>>(d_ev + (size_t)level * nb);
+    DLA_LAUNCHED();
+    if (level == 0) {
+      evidence_level_kernel<<<nb, 1024, 0, rt.stream>>>(d_ev + (size_t)md * nb);
+      DLA_LAUNCHED();
+    }
+    for (int b = 0; b < nb; ++b)
+      if (h_alive[(size_t)b * 4]) cat->gram_flops += (double)ns * (472.0 * sl.n_b[b] + 3.1e3);
+  }
+  {
+    dim3 grid(md, nb);
+    map_kernel<<<grid, 256, 0, rt.stream>>>(d_map);
+    DLA_LAUNCHED();
+    gather_evidences_kernel<<<(nb + 127) / 128, 128, 0, rt.stream>>>(d_gather, nb);
+    DLA_LAUNCHED();
+    model_selection_kernel<<<(nb + 127) / 128, 128, 0, rt.stream>>>(
+        d_log_priors_in + (size_t)q0 * m, res + RL.log_lik, nb, md, res + RL.log_priors, res + RL.log_post,
+        res + RL.model_post, res + RL.p_dla, res + RL.p_no_dla);
+    DLA_LAUNCHED();
+    if (o->base_sample_inds && md > 1) {
+      dim3 tgrid((S + 255) / 256, nb);
+      transpose_inds_kernel<<<tgrid, 256, 0, rt.stream>>>(cat->rows.p, S, md, cat->inds_t.p);
+      DLA_LAUNCHED();
+    }
+  }
+  // ---- results -> the slot's page-locked staging (the host picks them up one batch later) ----------------
+  DLA_CUDA(cudaMemcpyAsync(sl.h_res.p, res, sizeof(double) * RL.total, cudaMemcpyDeviceToHost, rt.stream));
+  DLA_CUDA(cudaMemcpyAsync(sl.h_alive.p, cat->alive.p, sizeof(int) * nb * 4, cudaMemcpyDeviceToHost, rt.stream));
+  if (o->sample_log_likelihoods_dla)
+    DLA_CUDA(cudaMemcpyAsync(sl.h_sample_dla.p, cat->sample_ll_dla.p, sizeof(double) * nb * S * md, cudaMemcpyDeviceToHost, rt.stream));
+  if (o->sample_log_likelihoods_lls)
+    DLA_CUDA(cudaMemcpyAsync(sl.h_sample_sub.p, cat->sample_ll_sub.p, sizeof(double) * nb * S, cudaMemcpyDeviceToHost, rt.stream));
+  if (o->base_sample_inds && md > 1)
+    DLA_CUDA(cudaMemcpyAsync(sl.h_inds.p, cat->inds_t.p, sizeof(int32_t) * nb * S * (md - 1), cudaMemcpyDeviceToHost, rt.stream));
+  DLA_CUDA(cudaEventRecord(sl.ev_done, rt.stream));
+  return 0;
+}
+
+// ---- pipeline stage: results of batch `bi` from the slot's staging into the caller's arrays ----------------------
+static int cat_consume(dla_catalogue* cat, int bi, dla_catalogue_outputs* o) {
+  CatSlot& sl = cat->slot[bi & 1];
+  const size_t S = cat->S, md = cat->max_dlas, m = 2 + md, B = cat->B;
+  const size_t nb = sl.nb, q0 = sl.q0;
+  DLA_CUDA(cudaEventSynchronize(sl.ev_done));
+  const CatResLayout RL = cat_res_layout(B, m, md);
+  const double* r = sl.h_res.p;
+  auto put = [&](double* dst, size_t dst_off, size_t src_off, size_t count) {
+    if (dst) memcpy(dst + dst_off, r + src_off, sizeof(double) * count);
+  };
+  put(o->log_priors, q0 * m, RL.log_priors, nb * m);
+  put(o->log_likelihoods, q0 * m, RL.log_lik, nb * m);
+  put(o->log_posteriors, q0 * m, RL.log_post, nb * m);
+  put(o->model_posteriors, q0 * m, RL.model_post, nb * m);
+  put(o->p_dlas, q0, RL.p_dla, nb);
+  put(o->p_no_dlas, q0, RL.p_no_dla, nb);
+  put(o->MAP_z_dlas, q0 * md * md, RL.map_z, nb * md * md);
+  put(o->MAP_log_nhis, q0 * md * md, RL.map_lognhi, nb * md * md);
+  if (o->sample_log_likelihoods_dla)
+    memcpy(o->sample_log_likelihoods_dla + q0 * S * md, sl.h_sample_dla.p, sizeof(double) * nb * S * md);
+  if (o->sample_log_likelihoods_lls)
+    memcpy(o->sample_log_likelihoods_lls + q0 * S, sl.h_sample_sub.p, sizeof(double) * nb * S);
+  if (o->base_sample_inds && md > 1)
+    memcpy(o->base_sample_inds + q0 * S * (md - 1), sl.h_inds.p, sizeof(int32_t) * nb * S * (md - 1));
+  for (size_t b = 0; b < nb; ++b) {
+    if (o->min_z_dlas) o->min_z_dlas[q0 + b] = sl.zmin_b[b];
+    if (o->max_z_dlas) o->max_z_dlas[q0 + b] = sl.zmax_b[b];
+    if (o->num_pixels) o->num_pixels[q0 + b] = sl.n_b[b];
+    if (o->status) o->status[q0 + b] = sl.h_alive.p[b * 4 + 1];
+  }
+  float ms = 0.f;
+  DLA_CUDA(cudaEventElapsedTime(&ms, sl.ev_v0, sl.ev_v1));
+  cat->voigt_ms += ms;
+  for (size_t level = 0; level < md; ++level) {
+    DLA_CUDA(cudaEventElapsedTime(&ms, sl.ev_lk[2 * level], sl.ev_lk[2 * level + 1]));
+    cat->gram_ms += ms;
+  }
+  return 0;
+}
+
+static int cat_run(dla_catalogue* cat, const CatSource& src, const double* d_log_priors_in, dla_catalogue_outputs* o) {
+  Runtime& rt = runtime();
+  const size_t cap = src.max_n_raw;
+  int rc = cat_ensure_workspace(cat, cap, !src.on_device, o);
   if (rc) return rc;
   cat->total_ms = cat->gram_ms = cat->voigt_ms = cat->gram_flops = 0;
   const long long launches_before = rt.launches;
-  PrepParams P = to_prep_params(&cat->params, 1);
-
-  cudaEvent_t e_call0 = cat_event(cat, 0), e_call1 = cat_event(cat, 1);
-  DLA_CUDA(cudaEventRecord(e_call0, rt.stream));
-
-  std::vector<PrepTask> h_prep;
-  std::vector<AbsorptionGrid> h_grid;
-  std::vector<LikelihoodSpectrum> h_lk;
-  std::vector<EvidenceLevel> h_ev;
-  std::vector<MapTask> h_map;
-  std::vector<GatherTask> h_gather;
-  std::vector<double> h_scalars;
-  std::vector<int> h_alive;
-
-  for (int q0 = 0; q0 < cat->Q; q0 += cat->B) {
-    const int nb = std::min(cat->B, cat->Q - q0);
-    size_t ev_i = 2;
-    // ---- 1. prepare --------------------------------------------------------------------------
-    h_prep.resize(nb);
-    for (int b = 0; b < nb; ++b) {
-      const int64_t off = cat->pix_off[q0 + b];
-      PrepTask t;
-      t.X = nullptr;
-      t.Wobs = cat->wl.p + off;
-      t.Y = cat->flux.p + off;
-      t.V = cat->var.p + off;
-      t.mask = cat->mask.p + off;
-      t.n_raw = (int)(cat->pix_off[q0 + b + 1] - off);
-      t.z_qso = cat->z_qsos[q0 + b];
-      t.ind_unmasked = cat->ind_unmasked.p + b * cap;
-      t.ind = cat->ind.p + b * cap;
-      t.x = cat->x.p + b * cap;
-      t.y = cat->y.p + b * cap;
-      t.v = cat->v.p + b * cap;
-      t.this_wl = cat->this_wl.p + b * cap;
-      t.mu = cat->mu.p + b * cap;
-      t.omega2 = cat->omega2.p + b * cap;
-      t.M = cat->M.p + b * cap * LK_K;
-      t.uidx = cat->uidx.p + b * cap;
-      t.unmasked_wl = cat->unmasked_wl.p + b * cap;
-      t.wl_abs = cat->wl_abs.p + b * (cap + 2 * w);
-      t.padded_wl = cat->padded_wl.p + b * (cap + 2 * w);
-      t.scratch = cat->scratch.p + b * cap;
-      t.scalars = cat->scalars.p + (size_t)b * 8;
-      h_prep[b] = t;
-    }
-    DLA_CUDA(cudaMemcpyAsync(cat->prep_desc.p, h_prep.data(), sizeof(PrepTask) * nb, cudaMemcpyHostToDevice, rt.stream));
-    cudaEvent_t e_begin = cat_event(cat, ev_i++);
-    DLA_CUDA(cudaEventRecord(e_begin, rt.stream));
-    prepare_spectrum_kernel<<<nb, 256, 0, rt.stream>>>(cat->prep_desc.p, cat->model->dev, P);
-    DLA_LAUNCHED();
-    h_scalars.resize((size_t)nb * 8);
-    DLA_CUDA(cat->scalars.download(h_scalars.data(), (size_t)nb * 8, rt.stream));
-    DLA_CUDA(cudaStreamSynchronize(rt.stream));
-
-    // ---- 2. sizes, cache layout, descriptors ---------------------------------------------------
-    std::vector<int> n_b(nb), nu_b(nb), ld_b(nb);
-    std::vector<size_t> cache_off(nb), prod_off(nb), basis_off(nb);
-    size_t cache_total = 0, prod_total = 0, basis_total = 0;
-    int max_n_abs = 1, max_basis_rows = LK_KC;
-    for (int b = 0; b < nb; ++b) {
-      nu_b[b] = (int)h_scalars[(size_t)b * 8 + 0];
-      n_b[b] = (int)h_scalars[(size_t)b * 8 + 1];
-      ld_b[b] = (int)round_up(std::max(n_b[b], 1), 4);
-      cache_off[b] = cache_total;
-      cache_total += (size_t)(2 * S + 1) * ld_b[b];
-      prod_off[b] = prod_total;
-      if (md >= 3) prod_total += (size_t)S * ld_b[b];
-      max_n_abs = std::max(max_n_abs, cat->params.broadening ? nu_b[b] + 2 * w : nu_b[b]);
-      const size_t brows = round_up((size_t)std::max(n_b[b], 1), LK_KC);
-      basis_off[b] = basis_total;
-      basis_total += brows * LK_PSTRIDE;
-      max_basis_rows = std::max(max_basis_rows, (int)brows);
-    }
-    DLA_CUDA(cat->cache.ensure(cache_total));
-    DLA_CUDA(cat->prod.ensure(prod_total));
-    DLA_CUDA(cat->basis.ensure(basis_total));
-    DLA_CUDA(cat->basis_desc.ensure(nb));
-    std::vector<GramBasisTask> h_basis(nb);
-    for (int b = 0; b < nb; ++b) {
-      h_basis[b].M = h_prep[b].M;
-      h_basis[b].P = cat->basis.p + basis_off[b];
-      h_basis[b].n = n_b[b];
-    }
-    DLA_CUDA(cudaMemcpyAsync(cat->basis_desc.p, h_basis.data(), sizeof(GramBasisTask) * nb, cudaMemcpyHostToDevice, rt.stream));
-
-    h_grid.resize(nb);
-    h_lk.assign((size_t)nb * md, LikelihoodSpectrum());
-    h_ev.assign((size_t)nb * (md + 1), EvidenceLevel());
-    h_map.resize(nb);
-    h_gather.resize(nb);
-    h_alive.assign((size_t)nb * 4, 0);
-    for (int b = 0; b < nb; ++b) {
-      const bool usable = n_b[b] >= 1 && isfinite(h_scalars[(size_t)b * 8 + 3]) && isfinite(h_scalars[(size_t)b * 8 + 4]);
-      h_alive[(size_t)b * 4 + 0] = usable ? 1 : 0;
-      h_alive[(size_t)b * 4 + 1] = usable ? 0 : 1;  // status 1: nothing to model
-      h_alive[(size_t)b * 4 + 2] = usable ? 1 : 0;
-      double* cache_b = cat->cache.p + cache_off[b];
-      AbsorptionGrid g;
-      g.wl = h_prep[b].wl_abs;
-      g.uidx = h_prep[b].uidx;
-      g.qmap = cat->qmap.p + (size_t)b * cap;
-      g.out = cache_b;
-      g.n_in = cat->params.broadening ? nu_b[b] + 2 * w : nu_b[b];
-      g.n_out = n_b[b];
-      g.ld = ld_b[b];
-      g.num_samples = usable ? 2 * S : 0;
-      g.z = cat->z_samples.p + (size_t)b * 2 * S;
-      g.nhi = cat->nhi_all.p;
-      g.pair_offset = cat->paired_offsets ? S : 0;
-      g.lls_break = 0;
-      h_grid[b] = g;
-      for (int level = 0; level < md; ++level) {
-        LikelihoodSpectrum d;
-        d.y = h_prep[b].y;
-        d.v = h_prep[b].v;
-        d.mu = h_prep[b].mu;
-        d.omega2 = h_prep[b].omega2;
-        d.M = h_prep[b].M;
-        d.P = cat->basis.p + basis_off[b];
-        d.cache = cache_b;
-        d.rows0 = nullptr;
-        d.alive = cat->alive.p + (size_t)b * 4;
-        d.n = n_b[b];
-        d.ld = ld_b[b];
-        d.row0 = 0;
-        if (level == 0) {  // DLA + subDLA + null rows in one go
-          d.base0 = cache_b;
-          d.rows = nullptr;
-          d.prod_out = nullptr;
-          d.out = cat->raw_ll0.p + (size_t)b * (2 * S + 1);
-          d.num_samples = 2 * S + 1;
-          d.num_rows = 1;
-          d.row_stride = 0;
-        } else {
-          // running product of the previous level (row s) x profile of the newly drawn absorber
-          double* prod_b = cat->prod.p + prod_off[b];
-          d.base0 = level == 1 ? cache_b : prod_b;
-          d.rows = cat->rows.p + (size_t)b * S * md + (size_t)level * S;
-          d.prod_out = (level + 1 < md) ? prod_b : nullptr;
-          d.out = cat->raw_ll.p + (size_t)b * S;
-          d.num_samples = S;
-          d.num_rows = 2;
-          d.row_stride = S;
-        }
-        h_lk[(size_t)level * nb + b] = d;
-        EvidenceLevel e;
-        e.raw_ll = level == 0 ? cat->raw_ll0.p + (size_t)b * (2 * S + 1) : cat->raw_ll.p + (size_t)b * S;
-        e.sample_ll = cat->sample_ll_dla.p + (size_t)b * S * md + level;
-        e.ll_stride = md;
-        e.z_samples = cat->z_samples.p + (size_t)b * 2 * S;
-        e.base_inds = cat->rows.p + (size_t)b * S * md + S;
-        e.base_out = (level + 1 < md) ? cat->rows.p + (size_t)b * S * md + (size_t)(level + 1) * S : nullptr;
-        e.uniforms = (level + 1 < md) ? cat->uniforms.p + (size_t)level * S : nullptr;
-        e.log_evidence = cat->log_ev_dla.p + (size_t)b * md + level;
-        e.cdf_scratch = cat->cdf.p + (size_t)b * S;
-        e.alive = cat->alive.p + (size_t)b * 4;
-        e.status = cat->alive.p + (size_t)b * 4 + 1;
-        e.S = S;
-        e.level = level;
-        e.min_z_separation = cat->params.min_z_separation;
-        h_ev[(size_t)level * nb + b] = e;
-      }
-      {  // subDLA model: one level, no resampling (subdla_gp.py, max_dlas = 1)
-        EvidenceLevel e;
-        e.raw_ll = cat->raw_ll0.p + (size_t)b * (2 * S + 1) + S;
-        e.sample_ll = cat->sample_ll_sub.p + (size_t)b * S;
-        e.ll_stride = 1;
-        e.z_samples = cat->z_samples.p + (size_t)b * 2 * S + S;
-        e.base_inds = nullptr;
-        e.base_out = nullptr;
-        e.uniforms = nullptr;
-        e.log_evidence = cat->log_ev_sub.p + b;
-        e.cdf_scratch = nullptr;
-        e.alive = cat->alive.p + (size_t)b * 4 + 2;  // not affected by the DLA model's early exit
-        e.status = nullptr;
-        e.S = S;
-        e.level = 0;
-        e.min_z_separation = cat->params.min_z_separation;
-        h_ev[(size_t)md * nb + b] = e;
-      }
-      MapTask mt;
-      mt.sample_ll = cat->sample_ll_dla.p + (size_t)b * S * md;
-      mt.base_inds = cat->rows.p + (size_t)b * S * md + S;
-      mt.z_samples = cat->z_samples.p + (size_t)b * 2 * S;
-      mt.log_nhi = cat->dla_log_nhi.p;
-      mt.map_z = cat->map_z.p + (size_t)b * md * md;
-      mt.map_log_nhi = cat->map_lognhi.p + (size_t)b * md * md;
-      mt.map_ind = cat->map_ind.p + (size_t)b * md;
-      mt.S = S;
-      mt.max_dlas = md;
-      h_map[b] = mt;
-      GatherTask gt;
-      gt.raw_ll0 = cat->raw_ll0.p + (size_t)b * (2 * S + 1);
-      gt.log_ev_dla = cat->log_ev_dla.p + (size_t)b * md;
-      gt.log_ev_sub = cat->log_ev_sub.p + b;
-      gt.log_lik = cat->log_lik.p + (size_t)b * m;
-      gt.S = S;
-      gt.max_dlas = md;
-      h_gather[b] = gt;
-    }
-    DLA_CUDA(cudaMemcpyAsync(cat->grid_desc.p, h_grid.data(), sizeof(AbsorptionGrid) * nb, cudaMemcpyHostToDevice, rt.stream));
-    DLA_CUDA(cudaMemcpyAsync(cat->lk_desc.p, h_lk.data(), sizeof(LikelihoodSpectrum) * nb * md, cudaMemcpyHostToDevice, rt.stream));
-    DLA_CUDA(cudaMemcpyAsync(cat->ev_desc.p, h_ev.data(), sizeof(EvidenceLevel) * nb * (md + 1), cudaMemcpyHostToDevice, rt.stream));
-    DLA_CUDA(cudaMemcpyAsync(cat->map_desc.p, h_map.data(), sizeof(MapTask) * nb, cudaMemcpyHostToDevice, rt.stream));
-    DLA_CUDA(cudaMemcpyAsync(cat->gather_desc.p, h_gather.data(), sizeof(GatherTask) * nb, cudaMemcpyHostToDevice, rt.stream));
-    DLA_CUDA(cudaMemcpyAsync(cat->alive.p, h_alive.data(), sizeof(int) * nb * 4, cudaMemcpyHostToDevice, rt.stream));
-
-    // ---- 3. launches ---------------------------------------------------------------------------
-    cudaEvent_t e_begin2 = cat_event(cat, ev_i++);
-    DLA_CUDA(cudaEventRecord(e_begin2, rt.stream));
-    auto fill = [&](double* p, size_t count, double value) -> int {
-      fill_double_kernel<<<(unsigned)((count + 255) / 256), 256, 0, rt.stream>>>(p, count, value);
-      DLA_LAUNCHED();
-      return 0;
-    };
-    if ((rc = fill(cat->sample_ll_dla.p, (size_t)nb * S * md, nan))) return rc;
-    if ((rc = fill(cat->sample_ll_sub.p, (size_t)nb * S, nan))) return rc;
-    if ((rc = fill(cat->log_ev_dla.p, (size_t)nb * md, nan))) return rc;
-    if ((rc = fill(cat->log_ev_sub.p, (size_t)nb, nan))) return rc;
-    if ((rc = fill(cat->raw_ll0.p, (size_t)nb * (2 * S + 1), nan))) return rc;
-    {
-      int max_ld = 1;
-      for (int b = 0; b < nb; ++b) max_ld = std::max(max_ld, ld_b[b]);
-      const size_t work = std::max((size_t)S * md, (size_t)max_ld);
-      dim3 grid((unsigned)((work + 255) / 256), nb);
-      init_rows_kernel<<<grid, 256, 0, rt.stream>>>(cat->rows.p, S, md, cat->grid_desc.p);
-      DLA_LAUNCHED();
-    }
-    gram_basis_kernel<<<dim3((unsigned)((max_basis_rows + 7) / 8), nb), 256, 0, rt.stream>>>(cat->basis_desc.p);
-    DLA_LAUNCHED();
-    {
-      dim3 grid((2 * S + 255) / 256, nb);
-      z_samples_kernel<<<grid, 256, 0, rt.stream>>>(cat->scalars.p, 8, cat->dla_offsets.p, cat->sub_offsets.p, S, cat->z_samples.p);
-      DLA_LAUNCHED();
-    }
-    // profiles
-    cudaEvent_t e_v0 = cat_event(cat, ev_i++), e_v1 = cat_event(cat, ev_i++);
-    {
-      build_qmap_kernel<<<nb, 256, 0, rt.stream>>>(cat->grid_desc.p, cat->params.broadening);
-      DLA_LAUNCHED();
-      DLA_CUDA(cudaEventRecord(e_v0, rt.stream));
-      if ((rc = launch_voigt_grids(cat->grid_desc.p, cat->paired_offsets ? S : 2 * S, nb, cat->params.num_lines,
-                                   cat->params.broadening)))
-        return rc;
-      DLA_CUDA(cudaEventRecord(e_v1, rt.stream));
-    }
-    // levels
-    std::vector<std::pair<cudaEvent_t, cudaEvent_t>> lk_events;
-    for (int level = 0; level < md; ++level) {
-      cudaEvent_t e0 = cat_event(cat, ev_i++), e1 = cat_event(cat, ev_i++);
-      DLA_CUDA(cudaEventRecord(e0, rt.stream));
-      const int ns = level == 0 ? 2 * S + 1 : S;
-      dim3 grid((ns + LK_TS - 1) / LK_TS, nb);
-      sample_likelihood_kernel<<<grid, LK_THREADS, LK_SMEM_BYTES, rt.stream>>>(cat->lk_desc.p + (size_t)level * nb);
-      DLA_LAUNCHED();
-      DLA_CUDA(cudaEventRecord(e1, rt.stream));
-      lk_events.push_back({e0, e1});
-      evidence_level_kernel<<<nb, 1024, 0, rt.stream>>>(cat->ev_desc.p + (size_t)level * nb);
-      DLA_LAUNCHED();
-      if (level == 0) {
-        evidence_level_kernel<<<nb, 1024, 0, rt.stream>>>(cat->ev_desc.p + (size_t)md * nb);
-        DLA_LAUNCHED();
-      }
-      for (int b = 0; b < nb; ++b)
-        if (h_alive[(size_t)b * 4]) cat->gram_flops += (double)ns * (472.0 * n_b[b] + 3.1e3);
-    }
-    {
-      dim3 grid(md, nb);
-      map_kernel<<<grid, 256, 0, rt.stream>>>(cat->map_desc.p);
-      DLA_LAUNCHED();
-      gather_evidences_kernel<<<(nb + 127) / 128, 128, 0, rt.stream>>>(cat->gather_desc.p, nb);
-      DLA_LAUNCHED();
-      model_selection_kernel<<<(nb + 127) / 128, 128, 0, rt.stream>>>(
-          cat->log_priors_in.p + (size_t)q0 * m, cat->log_lik.p, nb, md, cat->log_priors.p, cat->log_post.p,
-          cat->model_post.p, cat->p_dla.p, cat->p_no_dla.p);
-      DLA_LAUNCHED();
-      if (o->base_sample_inds && md > 1) {
-        dim3 tgrid((S + 255) / 256, nb);
-        transpose_inds_kernel<<<tgrid, 256, 0, rt.stream>>>(cat->rows.p, S, md, cat->inds_t.p);
-        DLA_LAUNCHED();
-      }
-    }
-    cudaEvent_t e_end = cat_event(cat, ev_i++);
-    DLA_CUDA(cudaEventRecord(e_end, rt.stream));
-
-    // ---- 4. results back -------------------------------------------------------------------------
-    auto d2h = [&](void* dst, const void* src, size_t bytes) -> int {
-      DLA_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, rt.stream));
-      return 0;
-    };
-    if (o->log_priors && (rc = d2h(o->log_priors + (size_t)q0 * m, cat->log_priors.p, sizeof(double) * nb * m))) return rc;
-    if (o->log_likelihoods && (rc = d2h(o->log_likelihoods + (size_t)q0 * m, cat->log_lik.p, sizeof(double) * nb * m))) return rc;
-    if (o->log_posteriors && (rc = d2h(o->log_posteriors + (size_t)q0 * m, cat->log_post.p, sizeof(double) * nb * m))) return rc;
-    if (o->model_posteriors && (rc = d2h(o->model_posteriors + (size_t)q0 * m, cat->model_post.p, sizeof(double) * nb * m))) return rc;
-    if (o->p_dlas && (rc = d2h(o->p_dlas + q0, cat->p_dla.p, sizeof(double) * nb))) return rc;
-    if (o->p_no_dlas && (rc = d2h(o->p_no_dlas + q0, cat->p_no_dla.p, sizeof(double) * nb))) return rc;
-    if (o->MAP_z_dlas && (rc = d2h(o->MAP_z_dlas + (size_t)q0 * md * md, cat->map_z.p, sizeof(double) * nb * md * md))) return rc;
-    if (o->MAP_log_nhis && (rc = d2h(o->MAP_log_nhis + (size_t)q0 * md * md, cat->map_lognhi.p, sizeof(double) * nb * md * md))) return rc;
-    if (o->sample_log_likelihoods_dla &&
-        (rc = d2h(o->sample_log_likelihoods_dla + (size_t)q0 * S * md, cat->sample_ll_dla.p, sizeof(double) * nb * S * md)))
-      return rc;
-    if (o->sample_log_likelihoods_lls &&
-        (rc = d2h(o->sample_log_likelihoods_lls + (size_t)q0 * S, cat->sample_ll_sub.p, sizeof(double) * nb * S)))
-      return rc;
-    if (o->base_sample_inds && md > 1 &&
-        (rc = d2h(o->base_sample_inds + (size_t)q0 * S * (md - 1), cat->inds_t.p, sizeof(int32_t) * nb * S * (md - 1))))
-      return rc;
-    h_alive.resize((size_t)nb * 4);
-    if ((rc = d2h(h_alive.data(), cat->alive.p, sizeof(int) * nb * 4))) return rc;
-    DLA_CUDA(cudaStreamSynchronize(rt.stream));
-    for (int b = 0; b < nb; ++b) {
-      if (o->min_z_dlas) o->min_z_dlas[q0 + b] = h_scalars[(size_t)b * 8 + 5];
-      if (o->max_z_dlas) o->max_z_dlas[q0 + b] = h_scalars[(size_t)b * 8 + 6];
-      if (o->num_pixels) o->num_pixels[q0 + b] = n_b[b];
-      if (o->status) o->status[q0 + b] = h_alive[(size_t)b * 4 + 1];
-    }
-    // ---- timing ------------------------------------------------------------------------------------
-    float ms = 0.f;
-    (void)e_begin; (void)e_begin2; (void)e_end;
-    DLA_CUDA(cudaEventElapsedTime(&ms, e_v0, e_v1));
-    cat->voigt_ms += ms;
-    for (auto& pr : lk_events) {
-      DLA_CUDA(cudaEventElapsedTime(&ms, pr.first, pr.second));
-      cat->gram_ms += ms;
-    }
+  const PrepParams P = to_prep_params(&cat->params, 1);
+  const int nbatches = (src.Q + cat->B - 1) / cat->B;
+  for (CatSlot& sl : cat->slot) sl.prep_recorded = false;
+  DLA_CUDA(cudaEventRecord(cat->ev_call0, rt.stream));
+  // the copy stream must not run ahead of work queued before this call (log_priors upload, previous run)
+  DLA_CUDA(cudaStreamWaitEvent(rt.copy_stream, cat->ev_call0, 0));
+  nvtxRangePushA("dla_catalogue_run");
+  for (int bi = 0; bi < std::min(2, nbatches); ++bi) {
+    if (!src.on_device && (rc = cat_enqueue_upload(cat, src, bi))) return rc;
+    if ((rc = cat_enqueue_prep(cat, src, bi, P, cap))) return rc;
   }
+  for (int bi = 0; bi < nbatches; ++bi) {
+    char label[64];
+    snprintf(label, sizeof(label), "batch %d (spectra %d..%d)", bi, bi * cat->B, std::min(src.Q, (bi + 1) * cat->B) - 1);
+    nvtxRangePushA(label);
+    if ((rc = cat_enqueue_compute(cat, bi, cap, o, d_log_priors_in))) return rc;
+    if (bi >= 1 && (rc = cat_consume(cat, bi - 1, o))) return rc;
+    if (bi + 2 < nbatches) {
+      if (!src.on_device && (rc = cat_enqueue_upload(cat, src, bi + 2))) return rc;
+      if ((rc = cat_enqueue_prep(cat, src, bi + 2, P, cap))) return rc;
+    }
+    nvtxRangePop();
+  }
+  if ((rc = cat_consume(cat, nbatches - 1, o))) return rc;
+  nvtxRangePop();
   // whole call on the library stream: kernels, descriptor uploads, result copies and host gaps
-  DLA_CUDA(cudaEventRecord(e_call1, rt.stream));
-  DLA_CUDA(cudaEventSynchronize(e_call1));
+  DLA_CUDA(cudaEventRecord(cat->ev_call1, rt.stream));
+  DLA_CUDA(cudaEventSynchronize(cat->ev_call1));
   {
     float ms = 0.f;
-    DLA_CUDA(cudaEventElapsedTime(&ms, e_call0, e_call1));
+    DLA_CUDA(cudaEventElapsedTime(&ms, cat->ev_call0, cat->ev_call1));
     cat->total_ms = ms;
   }
   cat->launches = rt.launches - launches_before;
@@ -590,14 +771,48 @@ extern "C" int dla_catalogue_run_staged(dla_catalogue* cat, dla_catalogue_output
   return 0;
 }
 
+extern "C" int dla_catalogue_run_staged(dla_catalogue* cat, dla_catalogue_outputs* o) {
+  DLA_CHECK_READY();
+  DLA_REQUIRE(cat && o, "null pointer argument");
+  DLA_REQUIRE(cat->Q >= 1, "nothing staged");
+  DLA_REQUIRE(cat->device == runtime().device, "the catalogue lives on another device than the one selected by dla_init");
+  CatSource src;
+  src.on_device = true;
+  src.pix_off = cat->pix_off.data();
+  src.wl = cat->wl.p;
+  src.flux = cat->flux.p;
+  src.var = cat->var.p;
+  src.mask = cat->mask.p;
+  src.z_qsos = cat->z_qsos.data();
+  src.Q = cat->Q;
+  src.max_n_raw = cat->max_n_raw;
+  return cat_run(cat, src, cat->log_priors_in.p, o);
+}
+
 extern "C" int dla_catalogue_process(dla_catalogue* cat, int num_spectra, const int64_t* pixel_offsets,
                                      const double* wavelengths, const double* flux, const double* noise_variance,
                                      const uint8_t* pixel_mask, const double* z_qsos, const double* log_priors_in,
                                      dla_catalogue_outputs* outputs) {
-  int rc = dla_catalogue_stage(cat, num_spectra, pixel_offsets, wavelengths, flux, noise_variance, pixel_mask, z_qsos,
-                               log_priors_in);
-  if (rc) return rc;
-  return dla_catalogue_run_staged(cat, outputs);
+  DLA_CHECK_READY();
+  Runtime& rt = runtime();
+  DLA_REQUIRE(cat && pixel_offsets && wavelengths && flux && noise_variance && pixel_mask && z_qsos && log_priors_in && outputs,
+              "null pointer argument");
+  DLA_REQUIRE(cat->device == rt.device, "the catalogue lives on another device than the one selected by dla_init");
+  CatSource src;
+  if (int rc = cat_check_offsets(num_spectra, pixel_offsets, &src.max_n_raw)) return rc;
+  src.on_device = false;
+  src.pix_off = pixel_offsets;
+  src.wl = wavelengths;
+  src.flux = flux;
+  src.var = noise_variance;
+  src.mask = pixel_mask;
+  src.z_qsos = z_qsos;
+  src.Q = num_spectra;
+  const int m = 2 + cat->max_dlas;
+  // the host-side priors of this call; a staged catalogue keeps its own copy
+  DLA_CUDA(cat->log_priors_call.ensure((size_t)num_spectra * m));
+  DLA_CUDA(cat->log_priors_call.upload(log_priors_in, (size_t)num_spectra * m, rt.stream));
+  return cat_run(cat, src, cat->log_priors_call.p, outputs);
 }
 
 extern "C" int dla_catalogue_last_timing(const dla_catalogue* cat, double* total_ms, double* gram_ms, double* voigt_ms,

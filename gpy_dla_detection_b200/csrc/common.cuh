@@ -13,6 +13,7 @@ struct Runtime {
   int device = -1;
   bool ready = false;
   cudaStream_t stream = nullptr;
+  cudaStream_t copy_stream = nullptr;  // H2D of the next batch's spectra while the current batch computes
   cudaEvent_t ev_begin = nullptr, ev_end = nullptr;
   double last_kernel_ms = 0.0;
   long long launches = 0;
@@ -81,6 +82,30 @@ struct DevBuf {
   }
   cudaError_t download(T* host, size_t count, cudaStream_t s) const {
     return cudaMemcpyAsync(host, p, count * sizeof(T), cudaMemcpyDeviceToHost, s);
+  }
+};
+
+// page-locked host staging buffer (descriptor uploads and result read-backs that must not block the host)
+template <typename T>
+struct PinnedBuf {
+  T* p = nullptr;
+  size_t n = 0;
+  PinnedBuf() = default;
+  PinnedBuf(const PinnedBuf&) = delete;
+  PinnedBuf& operator=(const PinnedBuf&) = delete;
+  ~PinnedBuf() { release(); }
+  void release() {
+    if (p) cudaFreeHost(p);
+    p = nullptr;
+    n = 0;
+  }
+  cudaError_t ensure(size_t count) {
+    if (count <= n) return cudaSuccess;
+    release();
+    if (count == 0) count = 1;
+    cudaError_t e = cudaMallocHost(&p, count * sizeof(T));
+    if (e == cudaSuccess) n = count;
+    return e;
   }
 };
 

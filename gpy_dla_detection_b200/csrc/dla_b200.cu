@@ -11,6 +11,8 @@
 #include <string>
 #include <vector>
 
+#include <nvtx3/nvToolsExt.h>
+
 #include "common.cuh"
 #include "evidence_kernel.cuh"
 #include "likelihood_kernel.cuh"
@@ -49,10 +51,12 @@ static int init_device(int device) {
   if (prop.major < 10) return fail(std::string("device '") + prop.name + "' is not sm_100-class; this library is built for sm_100a only");
   if (rt.stream) {
     cudaStreamDestroy(rt.stream);
+    if (rt.copy_stream) cudaStreamDestroy(rt.copy_stream);
     cudaEventDestroy(rt.ev_begin);
     cudaEventDestroy(rt.ev_end);
   }
   DLA_CUDA(cudaStreamCreateWithFlags(&rt.stream, cudaStreamNonBlocking));
+  DLA_CUDA(cudaStreamCreateWithFlags(&rt.copy_stream, cudaStreamNonBlocking));
   DLA_CUDA(cudaEventCreate(&rt.ev_begin));
   DLA_CUDA(cudaEventCreate(&rt.ev_end));
   rt.device = device;
@@ -141,9 +145,11 @@ using namespace dla;
 struct dla_model {
   DevBuf<double> rest, mu, M, log_omega;
   ModelDev dev;
+  int device = -1;  // every handle remembers its device; calls check it against the one dla_init selected
 };
 
 struct dla_spectrum {
+  int device = -1;
   int n_raw = 0, n_u = 0, n = 0, k = 0, width = 0, broadening = 1, n_abs = 0, ld = 0;
   int lls_break = 0;  // profiles include the Lyman-limit break (voigt_lls.py)
   double z_qso = 0.0;
@@ -471,6 +477,7 @@ extern "C" int dla_model_create(const double* rest_wavelengths, const double* mu
   m->dev.log_beta = log_beta;
   m->dev.prev_tau_0 = prev_tau_0;
   m->dev.prev_beta = prev_beta;
+  m->device = rt.device;
   *out = m.release();
   return 0;
 }

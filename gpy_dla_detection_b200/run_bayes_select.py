@@ -226,10 +226,17 @@ class CatalogueProcessor:
         return out
 
 
+def _chunk_arrays(source, start: int, stop: int, read_spec: Callable, qso_list):
+    """(offsets, wl, fl, nv, pm) of spectra [start, stop): views of a preloaded store, or read + pack."""
+    if source is not None:
+        return source.chunk(start, stop)
+    return CatalogueProcessor.pack([read_spec(item) for item in qso_list[start:stop]])
+
+
 def process_qso(
     qso_list: List,
     z_qso_list: List,
-    read_spec: Callable,
+    read_spec: Optional[Callable] = None,
     max_dlas: int = 4,
     broadening: bool = True,
     plot_figures: bool = False,
@@ -239,25 +246,83 @@ def process_qso(
     model: Dict[str, np.ndarray] = None,
     dla_samples=None,
     subdla_samples=None,
-    keep_samples: bool = True,
-    batch_spectra: int = 64,
+    keep_samples: bool = False,
+    batch_spectra: int = 128,
+    chunk_spectra: int = 4096,
+    out_dir: Optional[str] = None,
+    out_filename: Optional[str] = None,
+    resume: bool = True,
+    preloaded=None,
+    rank: int = 0,
+    world_size: int = 1,
+    processor: Optional["CatalogueProcessor"] = None,
+    writer=None,
 ) -> Dict[str, np.ndarray]:
     """
-    Process every spectrum of `qso_list` (run_bayes_select.py:32-295).  `read_spec(item)`
-    must return (wavelengths, flux, noise_variance, pixel_mask) as the reference's readers do.
-    The learned model, prior and sample objects are passed in (the reference loads them from
-    .mat files that are not part of this repository) and the result arrays are returned
-    under the reference's HDF5 dataset names instead of being written to disk.
+    Process every spectrum of `qso_list` (run_bayes_select.py:32-295).
+
+    `read_spec(item)` returns (wavelengths, flux, noise_variance, pixel_mask) as the reference's
+    readers do (default: read_spec.read_spec, as in the reference); alternatively pass
+    `preloaded=` a preload.PreloadedSpectra store (qso_list may then be the store's own list).
+    The learned model, prior and sample objects are passed in (the reference loads them from .mat
+    files that are not part of this repository).
+
+    The catalogue streams through the device engine in chunks of `chunk_spectra` spectra: each chunk
+    is read (or mapped), processed and - when `out_dir` is given - written as one chunk file with a
+    manifest, so an interrupted run resumes at the first missing chunk (`resume=True`) and host
+    memory holds one chunk of spectra, never the catalogue.  With `out_dir`, the reference's output
+    file `processed_qsos_multi_meanflux.h5` (dataset names of run_bayes_select.py:248-295; `.npz`
+    with the same keys when h5py is not installed) is written at the end and its path is returned as
+    `out["output_file"]`.
+
+    Returns the per-quasar arrays under the reference's dataset names.  The per-sample arrays
+    (`sample_log_likelihoods_dla`, `base_sample_inds`, `sample_log_likelihoods_lls`: 0.3 MB per
+    quasar, 51 GB at 160k) are produced only with `keep_samples=True`; they are returned in memory
+    when no `out_dir` is given and otherwise live in the chunk files / the merged file only.
     """
     if plot_figures:
         raise NotImplementedError("plotting is outside the hot path")
+    from .catalogue_io import ChunkedCatalogueWriter
+
+    if read_spec is None and preloaded is None:
+        from .read_spec import read_spec as _default_read_spec  # the reference's default argument
+
+        read_spec = _default_read_spec
     params = params or Parameters()
-    proc = CatalogueProcessor(params, prior, model, dla_samples, subdla_samples, max_dlas, broadening,
-                              batch_spectra=batch_spectra)
-    spectra = [read_spec(item) for item in qso_list]
-    offsets, wl, fl, nv, pm = proc.pack(spectra)
-    out = proc.process(offsets, wl, fl, nv, pm, np.asarray(z_qso_list, dtype=np.float64), keep_samples=keep_samples)
-    out["z_qsos"] = np.asarray(z_qso_list, dtype=np.float64)
+    z_all = np.asarray(z_qso_list, dtype=np.float64)
+    Q = len(qso_list)
+    if z_all.shape != (Q,):
+        raise ValueError("qso_list and z_qso_list must have the same length")
+    if preloaded is not None and len(preloaded) != Q:
+        raise ValueError("the preloaded store holds %d spectra, qso_list has %d" % (len(preloaded), Q))
+    proc = processor or CatalogueProcessor(params, prior, model, dla_samples, subdla_samples, max_dlas, broadening,
+                                           batch_spectra=batch_spectra)
+    if writer is None and out_dir is not None:
+        writer = ChunkedCatalogueWriter(out_dir, qso_list, z_all, params, max_dlas, chunk_spectra, keep_samples, resume)
+    if writer is not None:
+        todo = writer.chunks(rank, world_size)
+    else:
+        nchunks = (Q + chunk_spectra - 1) // chunk_spectra
+        todo = [(i, i * chunk_spectra, min((i + 1) * chunk_spectra, Q)) for i in range(nchunks) if i % world_size == rank]
+
+    in_memory: Dict[str, List[np.ndarray]] = {}
+    for idx, start, stop in todo:
+        offsets, wl, fl, nv, pm = _chunk_arrays(preloaded, start, stop, read_spec, qso_list)
+        res = proc.process(offsets, wl, fl, nv, pm, z_all[start:stop], keep_samples=keep_samples)
+        if writer is not None:
+            writer.write_chunk(idx, res, update_manifest=(world_size == 1))
+        else:
+            for k, v in res.items():
+                in_memory.setdefault(k, []).append(v)
+    if writer is None:
+        out = {k: np.concatenate(v, axis=0) for k, v in in_memory.items()}
+        if world_size == 1:
+            out["z_qsos"] = z_all
+        return out
+    if world_size > 1:
+        return {"writer": writer}  # process_qso_sharded merges after the barrier
+    out = writer.load_merged()
+    out["output_file"] = writer.merge(out_filename)
     return out
 
 
@@ -267,45 +332,65 @@ def process_qso(
 # (num_quasars, ...) result arrays on rank 0 - the in-box replacement of the reference's SLURM
 # job array + sbatch_reunion merge (slurm/submit_gp_find_lls.sh, CDDF_analysis/sbatch_reunion.py:13-63).
 # ---------------------------------------------------------------------------------------------------
+def _dist_device(group=None):
+    """Tensors of a collective live on the GPU for NCCL and on the host for gloo."""
+    import torch
+    import torch.distributed as dist
+
+    return torch.device("cuda", torch.cuda.current_device()) if dist.get_backend(group) == "nccl" else torch.device("cpu")
+
+
 def gather_results(local: Dict[str, np.ndarray], num_items: int, rank: int, world_size: int,
                    group=None) -> Optional[Dict[str, np.ndarray]]:
     """
     Concatenate the per-rank result dictionaries in spectrum order on rank 0 (None elsewhere).
     Every array whose leading dimension is the rank's shard length is gathered; the shards
     must follow `shard_range`.  A rank with an empty shard passes an empty dictionary.
+
+    One `torch.distributed.gather` per array into preallocated tensors (no pickling of the data):
+    rank 0 - whose block-partition shard is never empty - announces the array names, dtypes and
+    trailing shapes; every rank pads its shard to the longest shard and rank 0 trims.
     """
     if world_size == 1:
         return local
+    import torch
     import torch.distributed as dist
 
     start, stop = shard_range(num_items, rank, world_size)
-    mine = {k: v for k, v in local.items()
+    mine = {k: np.ascontiguousarray(v) for k, v in local.items()
             if stop > start and isinstance(v, np.ndarray) and v.ndim >= 1 and v.shape[0] == stop - start}
-    parts = [None] * world_size if rank == 0 else None
-    dist.gather_object(mine, parts, dst=0, group=group)
-    if rank != 0:
-        return None
-    keys = None
-    for r, part in enumerate(parts):
-        a, b = shard_range(num_items, r, world_size)
-        if b == a:
-            continue
-        if keys is None:
-            keys = sorted(part.keys())
-        if sorted(part.keys()) != keys:
-            raise RuntimeError("rank %d returned a different set of result arrays" % r)
-        for k in keys:
-            if part[k].shape[0] != b - a:
-                raise RuntimeError("rank %d: array %s has %d rows for a shard of %d" % (r, k, part[k].shape[0], b - a))
-    if keys is None:
-        return {}
-    return {k: np.concatenate([part[k] for part in parts if part], axis=0) for k in keys}
+    spec = [[(k, mine[k].dtype.str, tuple(mine[k].shape[1:])) for k in sorted(mine)]] if rank == 0 else [None]
+    dist.broadcast_object_list(spec, src=0, group=group)  # names and shapes only: a few hundred bytes
+    spec = spec[0]
+    if stop > start and sorted(mine) != [k for k, _, _ in spec]:
+        raise RuntimeError("rank %d returned a different set of result arrays than rank 0" % rank)
+    dev = _dist_device(group)
+    longest = shard_range(num_items, 0, world_size)[1]  # rank 0 holds a longest shard
+    out = {} if rank == 0 else None
+    for key, dtype, tail in spec:
+        np_dtype = np.dtype(dtype)
+        buf = np.zeros((longest,) + tuple(tail), dtype=np_dtype)
+        if stop > start:
+            if mine[key].dtype != np_dtype or tuple(mine[key].shape[1:]) != tuple(tail):
+                raise RuntimeError("rank %d: array %s has dtype/shape %s%s, rank 0 has %s%s"
+                                   % (rank, key, mine[key].dtype, mine[key].shape[1:], np_dtype, tuple(tail)))
+            buf[: stop - start] = mine[key]
+        t = torch.from_numpy(buf).to(dev)
+        parts = [torch.empty_like(t) for _ in range(world_size)] if rank == 0 else None
+        dist.gather(t, parts, dst=0, group=group)
+        if rank == 0:
+            pieces = []
+            for r, part in enumerate(parts):
+                a, b = shard_range(num_items, r, world_size)
+                pieces.append(part[: b - a].cpu().numpy())
+            out[key] = np.concatenate(pieces, axis=0)
+    return out
 
 
 def process_qso_sharded(
     qso_list: List,
     z_qso_list: List,
-    read_spec: Callable,
+    read_spec: Optional[Callable] = None,
     max_dlas: int = 4,
     broadening: bool = True,
     *,
@@ -316,10 +401,21 @@ def process_qso_sharded(
     **kwargs,
 ) -> Optional[Dict[str, np.ndarray]]:
     """
-    `process_qso` over the ranks of an initialised torch.distributed job (one rank per GPU):
-    rank r reads and processes the spectra of shard_range(Q, r, world_size) on its own device
-    and rank 0 returns the whole catalogue (None on the other ranks).  `process_fn` defaults
-    to `process_qso`.
+    `process_qso` over the ranks of an initialised torch.distributed job (one rank per GPU); rank 0
+    returns the whole catalogue (None on the other ranks).  Spectra are independent, so there is no
+    collective on the data path.
+
+    * without `out_dir`: rank r processes the spectra of shard_range(Q, r, world_size) and the
+      per-quasar arrays are gathered on rank 0 (`gather_results`); per-sample arrays are gathered too
+      when `keep_samples=True` - use `out_dir` for large catalogues;
+    * with `out_dir=...`: the chunks of the run are dealt round-robin to the ranks, every rank writes its
+      own chunk files, and after a barrier rank 0 records them in the manifest and writes the merged
+      output file (the in-box replacement of the reference's SLURM job array + sbatch_reunion merge,
+      slurm/submit_gp_find_lls.sh, CDDF_analysis/sbatch_reunion.py:13-63).  Resume works across a
+      different number of ranks.
+
+    `process_fn` (default `process_qso`) is called as process_fn(sub_list, sub_z, read_spec, max_dlas,
+    broadening, **kwargs).
     """
     import os
 
@@ -329,9 +425,42 @@ def process_qso_sharded(
         world_size = int(os.environ.get("WORLD_SIZE", "1"))
     Q = len(qso_list)
     assert len(z_qso_list) == Q
-    start, stop = shard_range(Q, rank, world_size)
     fn = process_fn or process_qso
+    if kwargs.get("out_dir") is not None and process_fn is None:
+        if world_size == 1:
+            return fn(qso_list, z_qso_list, read_spec, max_dlas, broadening, **kwargs)
+        import torch.distributed as dist
+        from .catalogue_io import ChunkedCatalogueWriter
+
+        def make_writer(resume):
+            return ChunkedCatalogueWriter(kwargs["out_dir"], qso_list, z_qso_list, kwargs.get("params") or Parameters(),
+                                          max_dlas, kwargs.get("chunk_spectra", 4096), kwargs.get("keep_samples", False),
+                                          resume)
+
+        # rank 0 creates (or validates) the manifest; the others read it after the barrier, so every rank
+        # skips the same finished chunks
+        writer = make_writer(kwargs.get("resume", True)) if rank == 0 else None
+        dist.barrier(group=group)
+        if rank != 0:
+            writer = make_writer(True)
+        fn(qso_list, z_qso_list, read_spec, max_dlas, broadening, rank=rank, world_size=world_size, writer=writer,
+           **kwargs)
+        dist.barrier(group=group)  # every rank has written its chunk files
+        if rank != 0:
+            return None
+        writer.adopt_chunks_on_disk()
+        out = writer.load_merged()
+        out["output_file"] = writer.merge(kwargs.get("out_filename"))
+        return out
+    start, stop = shard_range(Q, rank, world_size)
     local = {}
     if stop > start:
-        local = fn(qso_list[start:stop], z_qso_list[start:stop], read_spec, max_dlas, broadening, **kwargs)
-    return gather_results(local, Q, rank, world_size, group)
+        kw = dict(kwargs)
+        if kw.get("preloaded") is not None:
+            kw["preloaded"] = kw["preloaded"].view(start, stop)
+        local = fn(qso_list[start:stop], z_qso_list[start:stop], read_spec, max_dlas, broadening, **kw)
+        local.pop("z_qsos", None)
+    out = gather_results(local, Q, rank, world_size, group)
+    if out is not None and world_size > 1:
+        out["z_qsos"] = np.asarray(z_qso_list, dtype=np.float64)
+    return out

@@ -272,7 +272,65 @@ def golden_lls():
     print("lls_golden.npz written", ev)
 
 
+# 20 of the 128 spectra tools/parity_sweep.py runs: every 8th, plus the four highest redshifts of the draw
+SWEEP_INDICES = tuple(sorted(set(range(0, 128, 8)) | set(int(i) for i in np.argsort(synthetic.sample_z_qsos(128, seed=12345))[-4:])))
+SWEEP_STRIDE = 8                         # every 8th sample log-likelihood is kept
+
+
+def _sha(a):
+    import hashlib
+
+    return hashlib.sha256(np.ascontiguousarray(a).tobytes()).hexdigest()
+
+
+def _sweep_one(i):
+    """One spectrum of the bench workload (bench.py / synthetic.make_workload, seed0 = 0) through the live reference."""
+    z_qsos = synthetic.sample_z_qsos(128, seed=12345)
+    out = run_reference(S=10000, z_qso=float(z_qsos[i]), seed=i)
+    ll = out["sample_log_likelihoods_dla"]
+    inds = out["base_sample_inds"]
+    return dict(
+        index=i, z_qso=out["z_qso"], reference_seconds=out["reference_seconds"],
+        log_priors=out["log_priors"], log_likelihoods=out["log_likelihoods"], log_posteriors=out["log_posteriors"],
+        model_posteriors=out["model_posteriors"], p_dla=out["p_dla"], p_no_dla=out["p_no_dla"],
+        MAP_z_dlas=out["MAP_z_dlas"], MAP_log_nhis=out["MAP_log_nhis"],
+        min_z_dla=out["min_z_dla"], max_z_dla=out["max_z_dla"],
+        ll_dla_strided=ll[::SWEEP_STRIDE], ll_lls_strided=out["sample_log_likelihoods_lls"][::SWEEP_STRIDE],
+        ll_dla_nan_sha=_sha(np.isnan(ll)), ll_dla_nan_count=int(np.isnan(ll).sum()),
+        base_inds_sha=_sha(inds.astype(np.int32)), base_inds_head=inds[:, :64].astype(np.int32),
+        base_inds_tail=inds[:, -64:].astype(np.int32),
+        ind_sha=_sha(out["ind"].astype(np.uint8)), ind_unmasked_sha=_sha(out["ind_unmasked"].astype(np.uint8)),
+        num_pixels=int(out["x"].shape[0]),
+    )
+
+
+def golden_bench_sweep(workers=None):
+    """
+    Compact live-reference results for 16 spectra OF THE BENCH WORKLOAD at the full published size
+    (S = 10 000, max_dlas = 4): evidences, posteriors, MAP arrays, every 8th sample log-likelihood,
+    the NaN pattern's hash, and hash + head/tail of base_sample_inds (VERDICT r1 task 1).
+    About 50 s per spectrum per core.
+    """
+    import multiprocessing as mp
+
+    workers = workers or min(os.cpu_count() or 1, len(SWEEP_INDICES))
+    with mp.get_context("fork").Pool(workers) as pool:
+        rows = pool.map(_sweep_one, SWEEP_INDICES, chunksize=1)
+    out = {"indices": np.array(SWEEP_INDICES), "stride": SWEEP_STRIDE}
+    for key in rows[0]:
+        if key == "index":
+            continue
+        vals = [r[key] for r in rows]
+        out[key] = np.array(vals) if not isinstance(vals[0], str) else np.array(vals, dtype="U64")
+    np.savez_compressed(os.path.join(HERE, "bench_sweep_S10000.npz"), **out)
+    print("bench_sweep_S10000.npz written; reference seconds per spectrum: %.1f mean" % float(np.mean(out["reference_seconds"])))
+    print("p_dla:", np.round(out["p_dla"], 4))
+
+
 if __name__ == "__main__":
+    if "--only-sweep" in sys.argv:
+        golden_bench_sweep()
+        sys.exit(0)
     if "--only-lls" in sys.argv:
         golden_lls()
         sys.exit(0)
