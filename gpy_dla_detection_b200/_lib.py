@@ -139,6 +139,7 @@ SIGNATURES = {
         c_int,
         [c_void_p, POINTER(ZqsoParamsStruct), c_int, POINTER(c_int64), _dp, _dp, _dp, _bp, _dp, c_int, _dp, _dp, _ip],
     ),
+    "dla_zqso_last_timing": (c_int, [_dp, _dp]),
     "dla_zqso_set_data": (
         c_int,
         [c_void_p, POINTER(ZqsoParamsStruct), _dp, _dp, _dp, _bp, c_int, c_double, _dp, _dp, _dp, _dp, _dp, _bp, _bp, _dp],

@@ -96,8 +96,9 @@ struct CatSlot {
   PinnedBuf<int> h_alive;               // [B][4]
   PinnedBuf<double> h_sample_dla, h_sample_sub;  // optional per-sample arrays
   PinnedBuf<int32_t> h_inds;
-  // bookkeeping of the batch in flight
-  int q0 = 0, nb = 0;
+  // bookkeeping: (q0, nb) of the batch whose prep is queued; (c_q0, c_nb) of the batch whose compute is queued - the
+  // slot's next prep is enqueued before the previous compute's results are consumed
+  int q0 = 0, nb = 0, c_q0 = 0, c_nb = 0;
   std::vector<int> n_b;
   std::vector<double> zmin_b, zmax_b;
   cudaEvent_t ev_upload = nullptr, ev_prep = nullptr, ev_done = nullptr, ev_v0 = nullptr, ev_v1 = nullptr;
@@ -432,6 +433,8 @@ static int cat_enqueue_compute(dla_catalogue* cat, int bi, size_t cap, const dla
   CatSlot& sl = cat->slot[bi & 1];
   const int S = cat->S, md = cat->max_dlas, m = 2 + md, w = cat->params.width;
   const int nb = sl.nb, q0 = sl.q0;
+  sl.c_nb = nb;
+  sl.c_q0 = q0;
   const size_t B = cat->B;
   const double nan = std::numeric_limits<double>::quiet_NaN();
   int rc = 0;
@@ -689,7 +692,7 @@ static int cat_enqueue_compute(dla_catalogue* cat, int bi, size_t cap, const dla
 static int cat_consume(dla_catalogue* cat, int bi, dla_catalogue_outputs* o) {
   CatSlot& sl = cat->slot[bi & 1];
   const size_t S = cat->S, md = cat->max_dlas, m = 2 + md, B = cat->B;
-  const size_t nb = sl.nb, q0 = sl.q0;
+  const size_t nb = sl.c_nb, q0 = sl.c_q0;
   DLA_CUDA(cudaEventSynchronize(sl.ev_done));
   const CatResLayout RL = cat_res_layout(B, m, md);
   const double* r = sl.h_res.p;

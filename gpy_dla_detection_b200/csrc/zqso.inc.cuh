@@ -4,7 +4,11 @@
 struct dla_zqso_model {
   DevBuf<double> rest, mu, mu_slope, M, M_slope;
   ZqsoModelDev dev;
+  int device = -1;
 };
+
+// timing of the last dla_zqso_inference call: kernels only (inputs resident) and the whole call
+static double g_zqso_kernel_ms = 0.0, g_zqso_total_ms = 0.0;
 
 extern "C" int dla_zqso_model_create(const double* rest_wavelengths, const double* mu, const double* M, int n_rest, int k,
                                      double bluewards_mu, double redwards_mu, double bluewards_sigma,
@@ -48,6 +52,7 @@ extern "C" int dla_zqso_model_create(const double* rest_wavelengths, const doubl
   d.redwards_mu = redwards_mu;
   d.bluewards_var = bluewards_sigma * bluewards_sigma;  // sigma ** 2 (zqso_gp.py:202,208)
   d.redwards_var = redwards_sigma * redwards_sigma;
+  m->device = rt.device;
   *out = m.release();
   return 0;
 }
@@ -125,6 +130,10 @@ extern "C" int dla_zqso_inference(const dla_zqso_model* model, const dla_zqso_pa
   DLA_CUDA(dmapi.alloc(chunk));
   DLA_CUDA(ddesc.alloc(chunk));
   std::vector<ZqsoSpectrum> h_desc(chunk);
+  cudaEvent_t e_k0, e_k1;
+  DLA_CUDA(cudaEventCreate(&e_k0));
+  DLA_CUDA(cudaEventCreate(&e_k1));
+  g_zqso_kernel_ms = 0.0;
   KernelTimer timer;
   DLA_CUDA(timer.begin());
   for (int q0 = 0; q0 < num_spectra; q0 += chunk) {
@@ -139,17 +148,31 @@ extern "C" int dla_zqso_inference(const dla_zqso_model* model, const dla_zqso_pa
     }
     DLA_CUDA(cudaMemcpyAsync(ddesc.p, h_desc.data(), sizeof(ZqsoSpectrum) * nb, cudaMemcpyHostToDevice, rt.stream));
     dim3 grid((S + ZQ_WARPS - 1) / ZQ_WARPS, nb);
+    DLA_CUDA(cudaEventRecord(e_k0, rt.stream));
     zqso_likelihood_kernel<<<grid, ZQ_WARPS * 32, smem, rt.stream>>>(ddesc.p, dz.p, S, model->dev, to_zqso_params(params),
                                                                      norm_cap, per_warp, dll.p);
     DLA_LAUNCHED();
     zqso_argmax_kernel<<<nb, 256, 0, rt.stream>>>(dll.p, S, dz.p, dzmap.p, dmapi.p);
     DLA_LAUNCHED();
+    DLA_CUDA(cudaEventRecord(e_k1, rt.stream));
     if (sample_log_likelihoods) DLA_CUDA(dll.download(sample_log_likelihoods + (size_t)q0 * S, (size_t)nb * S, rt.stream));
     if (z_map) DLA_CUDA(dzmap.download(z_map + q0, nb, rt.stream));
     if (map_index) DLA_CUDA(dmapi.download(map_index + q0, nb, rt.stream));
     DLA_CUDA(cudaStreamSynchronize(rt.stream));  // h_desc is reused by the next chunk
+    float ms = 0.f;
+    DLA_CUDA(cudaEventElapsedTime(&ms, e_k0, e_k1));
+    g_zqso_kernel_ms += ms;
   }
   DLA_CUDA(timer.end());
+  g_zqso_total_ms = rt.last_kernel_ms;
+  cudaEventDestroy(e_k0);
+  cudaEventDestroy(e_k1);
+  return 0;
+}
+
+extern "C" int dla_zqso_last_timing(double* kernel_ms, double* total_ms) {
+  if (kernel_ms) *kernel_ms = g_zqso_kernel_ms;
+  if (total_ms) *total_ms = g_zqso_total_ms;
   return 0;
 }
 

@@ -311,3 +311,30 @@ def make_zqso_spectrum(model: Dict[str, np.ndarray], z_qso: float, seed: int, nu
         noise_variance = np.where(ivar0, np.inf, noise_variance)
     flux = np.where(ivar0, 0.0, flux)
     return wavelengths, flux, noise_variance, ivar0 | bright
+
+
+# ----------------------------------------------------------------------------------------
+# the benchmark / parity-sweep workloads (bench.py, tools/parity_sweep.py, tests/golden/make_golden.py)
+# ----------------------------------------------------------------------------------------
+def make_workload(num_spectra: int, seed0: int = 0, num_dla_samples: int = 10000, num_lines: int = 3):
+    """
+    `num_spectra` synthetic BOSS-like spectra with the model, prior and sample arrays of a DLA catalogue run.
+    Spectrum i is make_spectrum(model, z_qsos[i], seed = seed0 * 1000003 + i), z_qsos drawn with seed 12345 + seed0.
+    Returns (params, model, prior, dla_arrays, subdla_arrays, z_qsos, spectra).
+    """
+    params = Parameters(num_dla_samples=num_dla_samples, num_lines=num_lines)
+    model = make_learned_model(0)
+    prior = SyntheticPrior(params)
+    dla = make_dla_sample_arrays(params)
+    sub = make_subdla_sample_arrays(params)
+    z_qsos = sample_z_qsos(num_spectra, seed=12345 + seed0)
+    spectra = [make_spectrum(model, z_qsos[i], seed=seed0 * 1000003 + i) for i in range(num_spectra)]
+    return params, model, prior, dla, sub, z_qsos, spectra
+
+
+def make_zqso_workload(num_spectra: int, seed0: int = 0):
+    """`num_spectra` spectra for the zQSO sweep: (model, z_true, spectra); spectrum i has seed seed0 * 1000003 + i."""
+    model = make_zqso_model(0)
+    z_true = sample_z_qsos(num_spectra, seed=777 + seed0)
+    spectra = [make_zqso_spectrum(model, float(z_true[i]), seed=seed0 * 1000003 + i) for i in range(num_spectra)]
+    return model, z_true, spectra

@@ -162,20 +162,31 @@ class ZGP(NullGP):
         self.z_map = float(out["z_map"][0])
         print("[Info] Z MAP = {:.3g}".format(self.z_map))
 
-    def inference_z_qsos(self, spectra: Sequence[Tuple[np.ndarray, np.ndarray, np.ndarray, np.ndarray]],
-                         sample_z_qsos: np.ndarray, keep_samples: bool = True) -> Dict[str, np.ndarray]:
-        """
-        The sweep for a list of spectra (wavelengths, flux, noise_variance, pixel_mask) in one call:
-        `z_map` (Q,), `map_index` (Q,) and, when keep_samples, `sample_log_likelihoods` (Q, S).
-        """
-        zs = _lib.f64(sample_z_qsos)
-        Q, S = len(spectra), zs.shape[0]
+    @staticmethod
+    def pack(spectra: Sequence[Tuple[np.ndarray, np.ndarray, np.ndarray, np.ndarray]]):
+        """List of (wavelengths, flux, noise_variance, pixel_mask) -> (offsets, wl, fl, nv, pm) ragged contiguous arrays."""
         lengths = np.array([len(sp[0]) for sp in spectra], dtype=np.int64)
         offsets = np.concatenate([[0], np.cumsum(lengths)]).astype(np.int64)
         wl = np.concatenate([_lib.f64(sp[0]) for sp in spectra])
         fl = np.concatenate([_lib.f64(sp[1]) for sp in spectra])
         nv = np.concatenate([_lib.f64(sp[2]) for sp in spectra])
         pm = np.concatenate([_lib.u8(sp[3]) for sp in spectra])
+        return offsets, wl, fl, nv, pm
+
+    def inference_z_qsos(self, spectra: Sequence[Tuple[np.ndarray, np.ndarray, np.ndarray, np.ndarray]],
+                         sample_z_qsos: np.ndarray, keep_samples: bool = True) -> Dict[str, np.ndarray]:
+        """
+        The sweep for a list of spectra (wavelengths, flux, noise_variance, pixel_mask) in one call:
+        `z_map` (Q,), `map_index` (Q,) and, when keep_samples, `sample_log_likelihoods` (Q, S).
+        """
+        return self.inference_packed(self.pack(spectra), sample_z_qsos, keep_samples)
+
+    def inference_packed(self, packed, sample_z_qsos: np.ndarray, keep_samples: bool = True) -> Dict[str, np.ndarray]:
+        """The sweep on ragged arrays as `pack` (or a preload.PreloadedSpectra chunk) lays them out."""
+        offsets, wl, fl, nv, pm = packed
+        offsets = np.ascontiguousarray(offsets, dtype=np.int64)
+        zs = _lib.f64(sample_z_qsos)
+        Q, S = offsets.shape[0] - 1, zs.shape[0]
         ll = np.empty((Q, S)) if keep_samples else None
         z_map = np.empty(Q)
         map_index = np.empty(Q, dtype=np.int32)
@@ -191,6 +202,13 @@ class ZGP(NullGP):
         if keep_samples:
             out["sample_log_likelihoods"] = ll
         return out
+
+    @staticmethod
+    def last_timing() -> Dict[str, float]:
+        """GPU milliseconds of the last sweep: the kernels alone (spectra resident in HBM) and the whole call."""
+        k, t = ctypes.c_double(), ctypes.c_double()
+        _lib.check(_lib.load_library().dla_zqso_last_timing(ctypes.byref(k), ctypes.byref(t)))
+        return dict(kernel_ms=k.value, total_ms=t.value)
 
     @property
     def this_noise(self):

@@ -214,6 +214,9 @@ int dla_zqso_inference(const dla_zqso_model* model, const dla_zqso_params* param
                        const int64_t* pixel_offsets, const double* wavelengths, const double* flux,
                        const double* noise_variance, const uint8_t* pixel_mask, const double* z_samples,
                        int S, double* sample_log_likelihoods, double* z_map, int32_t* map_index);
+/* timing of the last dla_zqso_inference call (CUDA events on the library stream): the kernels alone, i.e. with the
+ * spectra already resident in HBM, and the whole call including the host <-> device copies */
+int dla_zqso_last_timing(double* kernel_ms, double* total_ms);
 /* ZGP.set_data + get_interp at one redshift (zqso_gp.py:66-182), element-wise over the n_raw pixels:
  * x = X / (1 + z), normalised flux / variance, interpolated mu (n_raw) and M (n_raw, k) where cls == 1,
  * cls (0 none, 1 modelled, 2 bluewards, 3 redwards), in_window (the first `ind` of :132), this_median.
