@@ -11,7 +11,8 @@ from ctypes import POINTER, c_char_p, c_double, c_int, c_int32, c_int64, c_longl
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libdla_b200.so")
+# DLA_B200_LIB: developer override used for A/B runs of kernel variants (tools/); the product path is the in-tree build
+LIB_PATH = os.environ.get("DLA_B200_LIB") or os.path.join(_HERE, "libdla_b200.so")
 
 _dp = POINTER(c_double)
 _ip = POINTER(c_int32)
@@ -96,6 +97,7 @@ SIGNATURES = {
         [_dp, _dp, _dp, _dp, c_int, c_int, c_double, c_double, c_double, c_double, c_double, POINTER(c_void_p)],
     ),
     "dla_model_destroy": (c_int, [c_void_p]),
+    "dla_model_interp": (c_int, [c_void_p, c_int, _dp, _dp, c_int, c_double, _dp, _dp, _dp]),
     "dla_spectrum_create": (
         c_int,
         [c_void_p, POINTER(DLAParamsStruct), _dp, _dp, _dp, _bp, c_int, c_double, c_int, POINTER(c_void_p)],
@@ -140,6 +142,7 @@ SIGNATURES = {
         [c_void_p, POINTER(ZqsoParamsStruct), c_int, POINTER(c_int64), _dp, _dp, _dp, _bp, _dp, c_int, _dp, _dp, _ip],
     ),
     "dla_zqso_last_timing": (c_int, [_dp, _dp]),
+    "dla_zqso_force_generic_kernel": (c_int, [c_int]),
     "dla_zqso_set_data": (
         c_int,
         [c_void_p, POINTER(ZqsoParamsStruct), _dp, _dp, _dp, _bp, c_int, c_double, _dp, _dp, _dp, _dp, _dp, _bp, _bp, _dp],

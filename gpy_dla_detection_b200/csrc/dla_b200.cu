@@ -487,6 +487,36 @@ extern "C" int dla_model_destroy(dla_model* model) {
   return 0;
 }
 
+// NullGP.get_interp (null_gp.py:179-242) on caller-supplied pixels: x rest wavelengths (inside the model grid),
+// wavelengths observed, both (n); outputs this_mu (n), this_M (n, k) row-major, this_omega2 (n)
+extern "C" int dla_model_interp(const dla_model* model, int num_forest_lines, const double* x, const double* wavelengths,
+                                int n, double z_qso, double* this_mu, double* this_M, double* this_omega2) {
+  DLA_CHECK_READY();
+  Runtime& rt = runtime();
+  DLA_REQUIRE(model && x && wavelengths && this_mu && this_M && this_omega2, "null pointer argument");
+  DLA_REQUIRE(model->device == rt.device, "the model lives on another device than the one selected by dla_init");
+  DLA_REQUIRE(n >= 0, "negative length");
+  DLA_REQUIRE(num_forest_lines >= 1 && num_forest_lines <= LYMAN_NUM_LINES, "num_forest_lines must be in [1, 31]");
+  if (n == 0) return 0;
+  const int k = model->dev.k;
+  DevBuf<double> dx, dw, dmu, dM, dom;
+  DLA_CUDA(dx.alloc(n));
+  DLA_CUDA(dw.alloc(n));
+  DLA_CUDA(dmu.alloc(n));
+  DLA_CUDA(dM.alloc((size_t)n * k));
+  DLA_CUDA(dom.alloc(n));
+  DLA_CUDA(dx.upload(x, n, rt.stream));
+  DLA_CUDA(dw.upload(wavelengths, n, rt.stream));
+  interp_model_kernel<<<(n + 127) / 128, 128, 0, rt.stream>>>(model->dev, num_forest_lines, dx.p, dw.p, n, z_qso, dmu.p,
+                                                               dM.p, dom.p);
+  DLA_LAUNCHED();
+  DLA_CUDA(dmu.download(this_mu, n, rt.stream));
+  DLA_CUDA(dM.download(this_M, (size_t)n * k, rt.stream));
+  DLA_CUDA(dom.download(this_omega2, n, rt.stream));
+  DLA_CUDA(cudaStreamSynchronize(rt.stream));
+  return 0;
+}
+
 static PrepParams to_prep_params(const dla_params* p, int normalize) {
   PrepParams P;
   P.min_lambda = p->min_lambda;
@@ -515,6 +545,7 @@ extern "C" int dla_spectrum_create(const dla_model* model, const dla_params* par
   Runtime& rt = runtime();
   DLA_REQUIRE(model && params && X && Y && V && pixel_mask && out, "null pointer argument");
   DLA_REQUIRE(n_raw >= 1, "empty spectrum");
+  DLA_REQUIRE(model->device == rt.device, "the model lives on another device than the one selected by dla_init");
   DLA_REQUIRE(params->width == INSTRUMENT_WIDTH, "instrument profile width must be 3");
   DLA_REQUIRE(params->num_forest_lines >= 1 && params->num_forest_lines <= LYMAN_NUM_LINES,
               "num_forest_lines must be in [1, 31]");
@@ -527,6 +558,7 @@ extern "C" int dla_spectrum_create(const dla_model* model, const dla_params* par
   sp->broadening = params->broadening ? 1 : 0;
   sp->z_qso = z_qso;
   sp->from_raw = true;
+  sp->device = rt.device;
   DLA_CUDA(sp->X.alloc(n_raw));
   DLA_CUDA(sp->Y.alloc(n_raw));
   DLA_CUDA(sp->V.alloc(n_raw));
@@ -611,6 +643,7 @@ extern "C" int dla_spectrum_create_prepared(const double* y, const double* v, co
   sp->broadening = broadening ? 1 : 0;
   sp->n_abs = n_abs;
   sp->ld = (int)round_up(n, 4);
+  sp->device = rt.device;
   DLA_CUDA(sp->y.alloc(n));
   DLA_CUDA(sp->v.alloc(n));
   DLA_CUDA(sp->mu.alloc(n));
@@ -654,6 +687,7 @@ extern "C" int dla_spectrum_get(const dla_spectrum* sp, double* x, double* y, do
   DLA_CHECK_READY();
   Runtime& rt = runtime();
   DLA_REQUIRE(sp, "null spectrum");
+  DLA_REQUIRE(sp->device == rt.device, "the spectrum lives on another device than the one selected by dla_init");
   const size_t n = sp->n, nu = sp->n_u;
   if (x && sp->x.p) DLA_CUDA(sp->x.download(x, n, rt.stream));
   if (y) DLA_CUDA(sp->y.download(y, n, rt.stream));
@@ -711,6 +745,7 @@ extern "C" int dla_null_log_model_evidence(dla_spectrum* sp, double* out) {
   DLA_CHECK_READY();
   Runtime& rt = runtime();
   DLA_REQUIRE(sp && out, "null pointer argument");
+  DLA_REQUIRE(sp->device == rt.device, "the spectrum lives on another device than the one selected by dla_init");
   DLA_REQUIRE(sp->k == LK_K, "the batched likelihood path is built for k = 20");
   DLA_REQUIRE(sp->n >= 1, "spectrum has no modelled pixels");
   if (int rcb = ensure_basis(sp)) return rcb;
@@ -741,6 +776,7 @@ extern "C" int dla_sample_log_likelihoods(dla_spectrum* sp, const double* z_dlas
   DLA_CHECK_READY();
   Runtime& rt = runtime();
   DLA_REQUIRE(sp && z_dlas && nhis && out, "null pointer argument");
+  DLA_REQUIRE(sp->device == rt.device, "the spectrum lives on another device than the one selected by dla_init");
   DLA_REQUIRE(S >= 1 && k_dlas >= 1 && k_dlas <= LK_MAX_ROWS, "need S >= 1 and 1 <= k_dlas <= 8");
   DLA_REQUIRE(sp->k == LK_K, "the batched likelihood path is built for k = 20");
   DLA_REQUIRE(sp->n >= 1, "spectrum has no modelled pixels");
@@ -784,6 +820,7 @@ extern "C" int dla_absorption_k_dlas(dla_spectrum* sp, const double* z_dlas, con
   DLA_CHECK_READY();
   Runtime& rt = runtime();
   DLA_REQUIRE(sp && z_dlas && nhis && out, "null pointer argument");
+  DLA_REQUIRE(sp->device == rt.device, "the spectrum lives on another device than the one selected by dla_init");
   DLA_REQUIRE(k_dlas >= 1, "need at least one absorber");
   DLA_REQUIRE(sp->n >= 1, "spectrum has no modelled pixels");
   DLA_CUDA(sp->z_dev.ensure(k_dlas));
@@ -812,6 +849,7 @@ extern "C" int dla_log_model_evidences(dla_spectrum* sp, const double* z_samples
   DLA_CHECK_READY();
   Runtime& rt = runtime();
   DLA_REQUIRE(sp && z_samples && nhi_samples && log_evidences, "null pointer argument");
+  DLA_REQUIRE(sp->device == rt.device, "the spectrum lives on another device than the one selected by dla_init");
   DLA_REQUIRE(S >= 1 && max_dlas >= 1 && max_dlas <= LK_MAX_ROWS, "need S >= 1 and 1 <= max_dlas <= 8");
   DLA_REQUIRE(max_dlas == 1 || uniforms, "uniforms are required when max_dlas > 1");
   DLA_REQUIRE(sp->k == LK_K, "the batched likelihood path is built for k = 20");

@@ -60,7 +60,7 @@ constexpr int LK_NCOLS = LK_NBLK * 8;            // 240
 constexpr int LK_PSTRIDE = LK_NCOLS + 4;         // basis row stride (244 == 4 mod 16: conflict-free B loads)
 constexpr int LK_PROJ_COL0 = LK_NBLK_PAIR * 8;   // 216: first projection column
 constexpr int LK_WARPS = 8;
-constexpr int LK_THREADS = LK_WARPS * 32;        // 512
+constexpr int LK_THREADS = LK_WARPS * 32;        // 256
 constexpr int LK_PSTAGES = 2;                    // basis-panel ring (TMA)
 constexpr int LK_CTAS_PER_SM = 2;               // (64 x 32 tiles, 16 warps, 1 CTA/SM measured 3 % slower)
 constexpr int LK_EP_STRIDE = LK_TS + 1;          // epilogue smem: [col][sample], stride 65
@@ -646,11 +646,23 @@ sample_likelihood_kernel(const LikelihoodSpectrum* __restrict__ specs) {
     // collected a_ij - sum_k l_ik l_jk when it reached column j, had FMA chains of length j/2 in front of every
     // pivot; this phase is latency-bound, it runs next to the other CTA's DMMAs).  Entries above the diagonal of a
     // thread's rows are never read for a result; updating them costs nothing extra in SIMT.
+    // product of the pivots with its binary exponent pulled out every four pivots (integer pipe): 20 pivots of an
+    // unnormalised spectrum (v ~ 1e-30: pivots ~ 1e31) would overflow a plain product and turn a finite
+    // log-likelihood into -inf; a non-positive or non-finite pivot is left alone and poisons the logarithm below
     double piv_prod = 1.0;
+    int piv_exp = 0;
 #pragma unroll
     for (int j = 0; j < LK_K; ++j) {
       const double piv = __shfl_sync(0xffffffffu, j < 8 ? r0[j < 8 ? j : 0] : j < 16 ? r1[j < 16 ? j : 0] : r2[j], gbase + (j & 7));
       piv_prod *= piv;
+      if ((j & 3) == 3) {
+        const int hi = __double2hiint(piv_prod);
+        const int ex = (hi >> 20) & 0x7ff;
+        if (hi > 0 && ex != 0 && ex != 0x7ff) {
+          piv_exp += ex - 1023;
+          piv_prod = __hiloint2double(hi - ((ex - 1023) << 20), __double2loint(piv_prod));
+        }
+      }
       const double inv = fast_rsqrt(piv);
       if (j < 8) r0[j < 8 ? j : 0] *= inv;  // rows below j: column j of L (row 20: z_j)
       if (j < 16) r1[j < 16 ? j : 0] *= inv;
@@ -670,7 +682,9 @@ sample_likelihood_kernel(const LikelihoodSpectrum* __restrict__ specs) {
 #pragma unroll
       for (int k = 0; k < LK_K; k += 2) { zz0 = fma(r2[k], r2[k], zz0); zz1 = fma(r2[k + 1], r2[k + 1], zz1); }
       const double quad = s_sums[s * 3] - (zz0 + zz1);
-      const double log_det = fma(s_sums[s * 3 + 2], LK_LN2, log(s_sums[s * 3 + 1] * piv_prod));  // sum log d + 2 sum log L_ii
+      // sum log d + 2 sum log L_ii; a pivot product that is not a positive number (zero, negative, NaN) poisons the sample
+      const double pp = piv_prod > 0.0 ? piv_prod : __longlong_as_double(0x7ff8000000000000ll);
+      const double log_det = fma(s_sums[s * 3 + 2] + (double)piv_exp, LK_LN2, log(s_sums[s * 3 + 1] * pp));
       sp.out[tile_s0 + s] = -0.5 * (quad + log_det + (double)n * LK_LOG_2PI);
     }
   }

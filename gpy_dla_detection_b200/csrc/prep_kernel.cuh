@@ -104,6 +104,40 @@ __device__ __forceinline__ double total_optical_depth(double wl, double beta, do
   return total;
 }
 
+// NullGP.get_interp for one pixel (null_gp.py:179-242): interpolate mu, log omega and the k columns of M at rest
+// wavelength x, apply the Kim et al. mean-flux suppression at observed wavelength wl to mu and M, and rescale
+// omega^2 by the learned (tau_0, beta) Lyman-series factor.  Explicitly rounded operations: no FMA contraction.
+__device__ __forceinline__ void interp_model_pixel(const ModelDev& model, int num_forest_lines, double x, double wl,
+                                                   double z_qso, double beta2, double tau2, double c0, double* mu_out,
+                                                   double* omega2_out, double* M_out) {
+  const int j = interp_locate(model.rest_wavelengths, model.n_rest, x);
+  double mu = interp_eval(model.rest_wavelengths, model.mu, 1, model.n_rest, j, x);
+  const double log_omega = interp_eval(model.rest_wavelengths, model.log_omega, 1, model.n_rest, j, x);
+  double omega2 = exp(__dmul_rn(2.0, log_omega));
+  const double lya_abs = exp(-total_optical_depth(wl, model.prev_beta, model.prev_tau_0, z_qso, num_forest_lines));
+  mu = __dmul_rn(mu, lya_abs);
+  const double od2 = total_optical_depth(wl, beta2, tau2, z_qso, num_forest_lines);
+  const double scaling = __dadd_rn(__dsub_rn(1.0, exp(-od2)), c0);
+  omega2 = __dmul_rn(omega2, __dmul_rn(scaling, scaling));
+  omega2 = __dmul_rn(omega2, __dmul_rn(lya_abs, lya_abs));
+  *mu_out = mu;
+  *omega2_out = omega2;
+  for (int c = 0; c < model.k; ++c) {
+    const double mv = interp_eval(model.rest_wavelengths, model.M + c, model.k, model.n_rest, j, x);
+    M_out[c] = __dmul_rn(mv, lya_abs);
+  }
+}
+
+// NullGP.get_interp on an arbitrary set of pixels (x rest, wl observed), one thread per pixel
+__global__ void interp_model_kernel(ModelDev model, int num_forest_lines, const double* __restrict__ x,
+                                    const double* __restrict__ wl, int n, double z_qso, double* __restrict__ mu,
+                                    double* __restrict__ M, double* __restrict__ omega2) {
+  const int q = blockIdx.x * blockDim.x + threadIdx.x;
+  if (q >= n) return;
+  const double beta2 = exp(model.log_beta), tau2 = exp(model.log_tau_0), c0 = exp(model.log_c_0);
+  interp_model_pixel(model, num_forest_lines, x[q], wl[q], z_qso, beta2, tau2, c0, mu + q, omega2 + q, M + (size_t)q * model.k);
+}
+
 // block-wide exclusive scan of one int per thread (blockDim.x <= 1024)
 __device__ __forceinline__ int block_exclusive_scan(int val, int* s_warp, int& block_total) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -244,33 +278,23 @@ prepare_spectrum_kernel(const PrepTask* __restrict__ tasks, ModelDev model, Prep
 
   // ---- 3./4. interpolation + mean-flux suppression (null_gp.py:179-242) ---------------------
   const double beta2 = exp(model.log_beta), tau2 = exp(model.log_tau_0), c0 = exp(model.log_c_0);
-  for (int q = tid; q < n; q += blockDim.x) {
-    const double x = t.x[q];
-    const int j = interp_locate(model.rest_wavelengths, model.n_rest, x);
-    double mu = interp_eval(model.rest_wavelengths, model.mu, 1, model.n_rest, j, x);
-    const double log_omega = interp_eval(model.rest_wavelengths, model.log_omega, 1, model.n_rest, j, x);
-    double omega2 = exp(__dmul_rn(2.0, log_omega));
-    const double wl = t.this_wl[q];
-    const double lya_abs = exp(-total_optical_depth(wl, model.prev_beta, model.prev_tau_0, t.z_qso, P.num_forest_lines));
-    mu = __dmul_rn(mu, lya_abs);
-    const double od2 = total_optical_depth(wl, beta2, tau2, t.z_qso, P.num_forest_lines);
-    const double scaling = __dadd_rn(__dsub_rn(1.0, exp(-od2)), c0);
-    omega2 = __dmul_rn(omega2, __dmul_rn(scaling, scaling));
-    omega2 = __dmul_rn(omega2, __dmul_rn(lya_abs, lya_abs));
-    t.mu[q] = mu;
-    t.omega2[q] = omega2;
-    for (int c = 0; c < model.k; ++c) {
-      const double mv = interp_eval(model.rest_wavelengths, model.M + c, model.k, model.n_rest, j, x);
-      t.M[(size_t)q * model.k + c] = __dmul_rn(mv, lya_abs);
-    }
-  }
+  for (int q = tid; q < n; q += blockDim.x)
+    interp_model_pixel(model, P.num_forest_lines, t.x[q], t.this_wl[q], t.z_qso, beta2, tau2, c0, t.mu + q, t.omega2 + q,
+                       t.M + (size_t)q * model.k);
 
   // ---- 5. padded grid (null_gp.py:159-177) and z_DLA range (set_parameters.py:125-159) -------
   // min / max of the in-range observed wavelengths and of the modelled ones
   {
     double mn_u = INFINITY, mx_u = -INFINITY, mn_n = INFINITY, mx_n = -INFINITY;
     for (int i = tid; i < n_u; i += blockDim.x) { const double w = t.unmasked_wl[i]; mn_u = fmin(mn_u, w); mx_u = fmax(mx_u, w); }
-    for (int i = tid; i < n; i += blockDim.x) { const double w = t.this_wl[i]; mn_n = fmin(mn_n, w); mx_n = fmax(mx_n, w); }
+    // Parameters.min_z_dla / max_z_dla re-filter the wavelengths they are given by emitted(w, z_qso) in
+    // [min_lambda, max_lambda] (set_parameters.py:125-159); the samplers hand them this_wavelengths = x (1 + z_qso)
+    // (dla_gp.py:122-124), and x (1 + z) / (1 + z) can fall one ulp outside the range at either end
+    for (int i = tid; i < n; i += blockDim.x) {
+      const double w = t.this_wl[i];
+      const double rest = __ddiv_rn(w, zp1);
+      if (rest >= P.min_lambda && rest <= P.max_lambda) { mn_n = fmin(mn_n, w); mx_n = fmax(mx_n, w); }
+    }
     for (int off = 16; off > 0; off >>= 1) {
       mn_u = fmin(mn_u, __shfl_xor_sync(0xffffffffu, mn_u, off));
       mx_u = fmax(mx_u, __shfl_xor_sync(0xffffffffu, mx_u, off));

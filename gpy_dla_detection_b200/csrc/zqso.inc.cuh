@@ -2,13 +2,14 @@
 // Reference: ZGP (gpy_dla_detection/zqso_gp.py).
 
 struct dla_zqso_model {
-  DevBuf<double> rest, mu, mu_slope, M, M_slope;
+  DevBuf<double> rest, mu, mu_slope, M, M_slope, MS;
   ZqsoModelDev dev;
   int device = -1;
 };
 
 // timing of the last dla_zqso_inference call: kernels only (inputs resident) and the whole call
 static double g_zqso_kernel_ms = 0.0, g_zqso_total_ms = 0.0;
+static int g_zqso_force_generic = 0;  // tests: run the generic (non-uniform grid) kernel on a uniform grid too
 
 extern "C" int dla_zqso_model_create(const double* rest_wavelengths, const double* mu, const double* M, int n_rest, int k,
                                      double bluewards_mu, double redwards_mu, double bluewards_sigma,
@@ -33,6 +34,10 @@ extern "C" int dla_zqso_model_create(const double* rest_wavelengths, const doubl
   zqso_slopes_kernel<<<(n_rest + 127) / 128, 128, 0, rt.stream>>>(m->rest.p, m->mu.p, M_in.p, n_rest, k, m->mu_slope.p,
                                                                    m->M.p, m->M_slope.p);
   DLA_LAUNCHED();
+  DLA_CUDA(m->MS.alloc((size_t)n_rest * ZQ_STRIDE * 2));
+  zqso_interleave_kernel<<<(n_rest + 127) / 128, 128, 0, rt.stream>>>(m->mu.p, m->mu_slope.p, m->M.p, m->M_slope.p, n_rest,
+                                                                       m->MS.p);
+  DLA_LAUNCHED();
   DLA_CUDA(cudaStreamSynchronize(rt.stream));
   // uniform grid (the published models: 910:0.25:3000): constant-time interval lookup
   const double dl = rest_wavelengths[1] - rest_wavelengths[0];
@@ -44,6 +49,7 @@ extern "C" int dla_zqso_model_create(const double* rest_wavelengths, const doubl
   d.mu_slope = m->mu_slope.p;
   d.M = m->M.p;
   d.M_slope = m->M_slope.p;
+  d.MS = m->MS.p;
   d.n_rest = n_rest;
   d.uniform = uniform ? 1 : 0;
   d.rest0 = rest_wavelengths[0];
@@ -92,6 +98,7 @@ extern "C" int dla_zqso_inference(const dla_zqso_model* model, const dla_zqso_pa
   DLA_REQUIRE(model && params && pixel_offsets && wavelengths && flux && noise_variance && pixel_mask && z_samples,
               "null pointer argument");
   DLA_REQUIRE(num_spectra >= 1 && S >= 1, "need at least one spectrum and one redshift sample");
+  DLA_REQUIRE(model->device == rt.device, "the model lives on another device than the one selected by dla_init");
   DLA_REQUIRE(params->normalization_min_lambda > 0 && params->normalization_max_lambda >= params->normalization_min_lambda,
               "bad normalisation window");
   const int64_t total = pixel_offsets[num_spectra];
@@ -109,6 +116,11 @@ extern "C" int dla_zqso_inference(const dla_zqso_model* model, const dla_zqso_pa
   const int per_warp = std::max(norm_cap, ZQ_TDIM * ZQ_TSTRIDE);
   const size_t smem = (size_t)ZQ_WARPS * per_warp * sizeof(double);
   DLA_CUDA(cudaFuncSetAttribute(zqso_likelihood_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  // uniform model grid (the published one): median pass + the v2 kernel; any other grid: the generic kernel
+  const bool v2 = model->dev.uniform != 0 && g_zqso_force_generic == 0;
+  const size_t smem_v2 = (size_t)ZQ_WARPS * ZQ2_PER_WARP * sizeof(double);
+  const size_t smem_med = (size_t)norm_cap * (sizeof(double) + sizeof(int));
+  DevBuf<double> dmed;
 
   DevBuf<double> dX, dY, dV, dz, dll, dzmap;
   DevBuf<uint8_t> dmask;
@@ -149,9 +161,19 @@ extern "C" int dla_zqso_inference(const dla_zqso_model* model, const dla_zqso_pa
     DLA_CUDA(cudaMemcpyAsync(ddesc.p, h_desc.data(), sizeof(ZqsoSpectrum) * nb, cudaMemcpyHostToDevice, rt.stream));
     dim3 grid((S + ZQ_WARPS - 1) / ZQ_WARPS, nb);
     DLA_CUDA(cudaEventRecord(e_k0, rt.stream));
-    zqso_likelihood_kernel<<<grid, ZQ_WARPS * 32, smem, rt.stream>>>(ddesc.p, dz.p, S, model->dev, to_zqso_params(params),
-                                                                     norm_cap, per_warp, dll.p);
-    DLA_LAUNCHED();
+    if (v2) {
+      DLA_CUDA(dmed.ensure((size_t)chunk * S));
+      dim3 mgrid((S + ZQ2_ZPB - 1) / ZQ2_ZPB, nb);
+      zqso_median_batch_kernel<<<mgrid, 256, smem_med, rt.stream>>>(ddesc.p, dz.p, S, to_zqso_params(params), norm_cap, dmed.p);
+      DLA_LAUNCHED();
+      zqso_likelihood_kernel_v2<<<grid, ZQ_WARPS * 32, smem_v2, rt.stream>>>(ddesc.p, dz.p, S, dmed.p, model->dev,
+                                                                            to_zqso_params(params), dll.p);
+      DLA_LAUNCHED();
+    } else {
+      zqso_likelihood_kernel<<<grid, ZQ_WARPS * 32, smem, rt.stream>>>(ddesc.p, dz.p, S, model->dev, to_zqso_params(params),
+                                                                       norm_cap, per_warp, dll.p);
+      DLA_LAUNCHED();
+    }
     zqso_argmax_kernel<<<nb, 256, 0, rt.stream>>>(dll.p, S, dz.p, dzmap.p, dmapi.p);
     DLA_LAUNCHED();
     DLA_CUDA(cudaEventRecord(e_k1, rt.stream));
@@ -167,6 +189,11 @@ extern "C" int dla_zqso_inference(const dla_zqso_model* model, const dla_zqso_pa
   g_zqso_total_ms = rt.last_kernel_ms;
   cudaEventDestroy(e_k0);
   cudaEventDestroy(e_k1);
+  return 0;
+}
+
+extern "C" int dla_zqso_force_generic_kernel(int on) {
+  g_zqso_force_generic = on ? 1 : 0;
   return 0;
 }
 

@@ -37,6 +37,7 @@ struct ZqsoModelDev {
   const double* mu_slope;   // n_rest - 1 : (mu[i+1] - mu[i]) / (rest[i+1] - rest[i])
   const double* M;          // n_rest x 24 (columns >= 20 are zero)
   const double* M_slope;    // (n_rest - 1) x 24
+  const double* MS;         // n_rest x 24 x 2 : (value, slope) pairs for the v2 kernel: M, then -mu in column 20
   int n_rest;
   int uniform;              // rest[i] == rest[0] + i * dl exactly
   double rest0, inv_dl;
@@ -324,6 +325,434 @@ zqso_likelihood_kernel(const ZqsoSpectrum* __restrict__ spectra, const double* _
     side_ll[side] = -0.5 * (q_tot + ld_tot + (double)c_tot * ZQ_LOG_2PI);
   }
   if (lane == 0) *out_ll = ll_window + side_ll[0] + side_ll[1];
+}
+
+// =====================================================================================================
+// Round-2 path for uniform model grids (the published 910:0.25:3000 grid): zqso_median_batch_kernel +
+// zqso_likelihood_kernel_v2.  What changed against the kernel above, and why (profiles/zqso_kernel_r01_ncu.txt:
+// tensor pipe 33 %, long-scoreboard 34 %, in-warp sort 10 %):
+//   * the nanmedian normalisation is a separate pass: a CTA takes 32 CONSECUTIVE redshift samples, whose
+//     normalisation windows overlap almost entirely (the window slides by about half a pixel per sample), sorts
+//     the union of the windows ONCE (bitonic, 256 threads) and every warp then picks its samples' medians by
+//     rank counting over the sorted union (ballot / popc) - instead of one 512-element bitonic sort per sample
+//     inside the warp that also has to feed the tensor pipe;
+//   * rest-frame coordinates without the division and the search: x = X (1/(1+z)), interval = trunc((x - x0)/dl),
+//     offset = x - (x0 + iv dl) - the interpolant is continuous, so a one-ulp difference in x moves the result by
+//     one ulp; the two DISCONTINUOUS decisions (window edges, zqso_gp.py:132 and :169-170) are still taken with
+//     the reference's own division, by binary search, once per sample;
+//   * the Gram operand is m' = m sqrt(1/v): A and B fragments of a diagonal-or-not block are the same three
+//     registers (the round-1 kernel carried m and m/v), and the per-pixel record (offset, sqrt weight, weighted
+//     residual, interval) goes through a 1 KB shared-memory buffer per warp instead of 7 shuffles per 4 pixels;
+//   * (value, slope) pairs are interleaved in one table: 3 LDG.128 per 4 pixels per lane instead of 6 LDG.64, issued
+//     one step ahead of their use, and the 3 FMA + 3 MUL that turn them into the next step's operands are threaded
+//     between the 6 DMMAs of the current step (measurement 3: a warp that carries its own
+//     scalar work between its DMMAs keeps the shared FP64 pipe busy; a warp that alternates phases does not);
+//   * the bordered 21 x 21 Cholesky runs in registers, one row per lane, rows broadcast by shuffles
+//     (the round-1 version walked shared memory with a square root per index).
+// =====================================================================================================
+constexpr int ZQ2_ZPB = 32;              // redshift samples per CTA of the median pass
+constexpr int ZQ2_REC = 4;               // doubles per pixel record: offset, sqrt weight, weighted residual, interval
+constexpr int ZQ2_PER_WARP = ZQ_TDIM * ZQ_TSTRIDE;  // 600 doubles: the T matrix; the two 32 x 4 record buffers overlay it
+
+// (value, slope) interleaved table for the v2 kernel: MS[i][24][2]; columns 0..19 = M, column 20 = -mu (so that the
+// lane that owns it forms the weighted residual with one FMA), columns 21..23 zero; the last row's slopes are 0
+__global__ void zqso_interleave_kernel(const double* mu, const double* mu_slope, const double* Mp, const double* Ms,
+                                       int n_rest, double* MS) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_rest) return;
+  const bool last = i + 1 >= n_rest;
+  for (int j = 0; j < ZQ_STRIDE; ++j) {
+    double v = Mp[(size_t)i * ZQ_STRIDE + j], sl = last ? 0.0 : Ms[(size_t)i * ZQ_STRIDE + j];
+    if (j == ZQ_K) { v = -mu[i]; sl = last ? 0.0 : -mu_slope[i]; }
+    MS[((size_t)i * ZQ_STRIDE + j) * 2] = v;
+    MS[((size_t)i * ZQ_STRIDE + j) * 2 + 1] = sl;
+  }
+}
+
+struct ZqWindow {
+  int lo, hi_end, bw_end, rw_begin;  // observed-frame window [lo, hi_end), bluewards [0, bw_end), redwards [rw_begin, n)
+  int wlo, whi;                      // modelled pixels: window and min_lambda <= X/(1+z) <= max_lambda (:169-170)
+  int nlo, nhi;                      // normalisation window (:142-148)
+};
+__device__ __forceinline__ ZqWindow zq_window(const double* X, int n_raw, double opz, const ZqsoParamsDev& prm) {
+  ZqWindow w;
+  const double max_pos = __dmul_rn(prm.max_lambda, opz), min_pos = __dmul_rn(prm.min_lambda, opz);
+  const double max_obs = fmin(max_pos, X[n_raw - 1]), min_obs = fmax(min_pos, X[0]);
+  w.lo = zq_bound(X, 0, n_raw, min_obs, true);
+  w.hi_end = zq_bound(X, 0, n_raw, max_obs, false);
+  w.bw_end = zq_bound(X, 0, n_raw, min_obs, false);
+  w.rw_begin = zq_bound(X, 0, n_raw, max_obs, true);
+  const int top = max(w.hi_end, w.lo);
+  w.wlo = zq_bound_rest(X, opz, w.lo, top, prm.min_lambda, false);  // first x >= min_lambda
+  w.whi = zq_bound_rest(X, opz, w.lo, top, prm.max_lambda, true);   // first x >  max_lambda
+  w.nlo = zq_bound_rest(X, opz, w.lo, top, prm.norm_min_lambda, false);
+  w.nhi = zq_bound_rest(X, opz, w.lo, top, prm.norm_max_lambda, true);
+  return w;
+}
+
+// CTA-wide bitonic sort of (key, tag) pairs in shared memory, ascending by key; n is a power of two
+__device__ __forceinline__ void zq_block_bitonic(double* key, int* tag, int n) {
+  for (int k = 2; k <= n; k <<= 1)
+    for (int j = k >> 1; j > 0; j >>= 1) {
+      for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        const int l = i ^ j;
+        if (l > i) {
+          const double a = key[i], b = key[l];
+          const bool up = (i & k) == 0;
+          if ((a > b) == up) {
+            key[i] = b; key[l] = a;
+            const int t = tag[i]; tag[i] = tag[l]; tag[l] = t;
+          }
+        }
+      }
+      __syncthreads();
+    }
+}
+
+// the value of rank `k` (0-based) among the sorted entries whose tag lies in [a, b); one warp
+__device__ __forceinline__ double zq_select_rank(const double* key, const int* tag, int n, int a, int b, int k, int lane) {
+  int seen = 0;
+  double val = 0.0;
+  for (int base = 0; base < n; base += 32) {
+    const int t = tag[base + lane];
+    const unsigned in = __ballot_sync(0xffffffffu, t >= a && t < b);
+    const int c = __popc(in);
+    if (k < seen + c) {
+      const int src = __fns(in, 0, k - seen + 1);  // lane of the (k - seen + 1)-th set bit
+      val = key[base + src];
+      break;
+    }
+    seen += c;
+  }
+  return val;
+}
+
+// grid = (ceil(S / 32), num_spectra), block = 256, dynamic smem = cap * 12 bytes; med_out [num_spectra][S]
+__global__ void __launch_bounds__(256)
+zqso_median_batch_kernel(const ZqsoSpectrum* __restrict__ spectra, const double* __restrict__ z_samples, int S,
+                         ZqsoParamsDev prm, int cap, double* __restrict__ med_out) {
+  extern __shared__ double zq_smem[];
+  double* key = zq_smem;
+  int* tag = reinterpret_cast<int*>(zq_smem + cap);
+  __shared__ int s_nlo[ZQ2_ZPB], s_nhi[ZQ2_ZPB];
+  __shared__ int s_union[2];
+  const ZqsoSpectrum sp = spectra[blockIdx.y];
+  const int s0 = blockIdx.x * ZQ2_ZPB;
+  const int nz = min(ZQ2_ZPB, S - s0);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const double inf = __longlong_as_double(0x7ff0000000000000LL);
+  const double qnan = __longlong_as_double(0x7ff8000000000000LL);
+  if (threadIdx.x < ZQ2_ZPB) {
+    int nlo = 0x7fffffff, nhi = 0;
+    if (threadIdx.x < nz) {
+      const ZqWindow w = zq_window(sp.X, sp.n_raw, __dadd_rn(1.0, z_samples[s0 + threadIdx.x]), prm);
+      nlo = w.nlo;
+      nhi = max(w.nhi, w.nlo);
+      s_nlo[threadIdx.x] = nlo;
+      s_nhi[threadIdx.x] = nhi;
+    }
+    // union of the non-empty windows
+    int ulo = nhi > nlo ? nlo : 0x7fffffff, uhi = nhi > nlo ? nhi : 0;
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+      ulo = min(ulo, __shfl_xor_sync(0xffffffffu, ulo, off));
+      uhi = max(uhi, __shfl_xor_sync(0xffffffffu, uhi, off));
+    }
+    if (threadIdx.x == 0) { s_union[0] = ulo; s_union[1] = uhi; }
+  }
+  __syncthreads();
+  const int ulo = s_union[0], uhi = s_union[1];
+  if (uhi <= ulo) {  // every window empty: nanmedian of nothing
+    if (threadIdx.x < nz) med_out[(size_t)blockIdx.y * S + s0 + threadIdx.x] = qnan;
+    return;
+  }
+  if (uhi - ulo <= cap) {
+    // one sort for the CTA's 32 samples; NaN flux gets tag -1 (np.nanmedian ignores it), pads too
+    for (int i = threadIdx.x; i < cap; i += blockDim.x) {
+      const int p = ulo + i;
+      double v = inf;
+      int t = -1;
+      if (p < uhi) {
+        const double yv = sp.Y[p];
+        if (!isnan(yv)) { v = yv; t = p; }
+      }
+      key[i] = v;
+      tag[i] = t;
+    }
+    __syncthreads();
+    zq_block_bitonic(key, tag, cap);
+    for (int zi = warp; zi < nz; zi += 8) {
+      const int a = s_nlo[zi], b = s_nhi[zi];
+      int count = 0;
+      for (int base = 0; base < cap; base += 32) {
+        const int t = tag[base + lane];
+        count += __popc(__ballot_sync(0xffffffffu, t >= a && t < b));
+      }
+      double med = qnan;
+      if (count > 0) {
+        const double hi = zq_select_rank(key, tag, cap, a, b, count >> 1, lane);
+        med = (count & 1) ? hi : (zq_select_rank(key, tag, cap, a, b, (count >> 1) - 1, lane) + hi) * 0.5;
+      }
+      if (lane == 0) med_out[(size_t)blockIdx.y * S + s0 + zi] = med;
+    }
+  } else {
+    // samples far apart (not a sorted sweep): one CTA-wide sort per sample
+    for (int zi = 0; zi < nz; ++zi) {
+      const int a = s_nlo[zi], b = s_nhi[zi];
+      __syncthreads();
+      for (int i = threadIdx.x; i < cap; i += blockDim.x) {
+        const int p = a + i;
+        double v = inf;
+        int t = -1;
+        if (p < b) {
+          const double yv = sp.Y[p];
+          if (!isnan(yv)) { v = yv; t = p; }
+        }
+        key[i] = v;
+        tag[i] = t;
+      }
+      __syncthreads();
+      zq_block_bitonic(key, tag, cap);
+      if (warp == 0) {
+        int count = 0;
+        for (int base = 0; base < cap; base += 32) count += __popc(__ballot_sync(0xffffffffu, tag[base + lane] >= 0));
+        double med = qnan;
+        if (count > 0) med = (count & 1) ? key[count >> 1] : (key[(count >> 1) - 1] + key[count >> 1]) * 0.5;
+        if (lane == 0) med_out[(size_t)blockIdx.y * S + s0 + zi] = med;
+      }
+    }
+  }
+}
+
+__device__ __forceinline__ void zq_dmma_pinned(double& c0, double& c1, double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+               : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
+}
+__device__ __forceinline__ double zq_fma_pinned(double a, double b, double c) {
+  double r;
+  asm volatile("fma.rn.f64 %0, %1, %2, %3;" : "=d"(r) : "d"(a), "d"(b), "d"(c));
+  return r;
+}
+__device__ __forceinline__ double zq_mul_pinned(double a, double b) {
+  double r;
+  asm volatile("mul.rn.f64 %0, %1, %2;" : "=d"(r) : "d"(a), "d"(b));
+  return r;
+}
+// 1 / sqrt(x): MUFU.RSQ64H seed and one cubic correction (see likelihood_kernel.cuh : fast_rsqrt)
+__device__ __forceinline__ double zq_rsqrt(double x) {
+  double y0;
+  asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y0) : "d"(x));
+  const double e = fma(-(x * y0), y0, 1.0);
+  const double p = fma(e, 0.375, 0.5) * e;
+  const double y = fma(y0, p, y0);
+  return (x > 1e-290 && x < 1e290) ? y : 1.0 / sqrt(x);
+}
+
+// grid = (ceil(S / 8), num_spectra), block = 256, dynamic smem = 8 * ZQ2_PER_WARP doubles.  Uniform model grid only.
+#ifndef ZQ2_MIN_CTAS
+#define ZQ2_MIN_CTAS 2
+#endif
+__global__ void __launch_bounds__(ZQ_WARPS * 32, ZQ2_MIN_CTAS)
+zqso_likelihood_kernel_v2(const ZqsoSpectrum* __restrict__ spectra, const double* __restrict__ z_samples, int S,
+                          const double* __restrict__ med_all, ZqsoModelDev model, ZqsoParamsDev prm,
+                          double* __restrict__ out /* [num_spectra][S] */) {
+  extern __shared__ double zq_smem[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int s = blockIdx.x * ZQ_WARPS + warp;
+  if (s >= S) return;
+  const ZqsoSpectrum sp = spectra[blockIdx.y];
+  double* buf = zq_smem + (size_t)warp * ZQ2_PER_WARP;
+  const double* __restrict__ X = sp.X;
+  const int n_raw = sp.n_raw;
+  const double z = z_samples[s];
+  const double opz = __dadd_rn(1.0, z);
+  const ZqWindow w = zq_window(X, n_raw, opz, prm);
+  const int wlo = max(w.lo, w.wlo), whi = min(w.hi_end, w.whi);
+  const double med = med_all[(size_t)blockIdx.y * S + s];
+  const double invmed = 1.0 / med;
+  const double invmed2 = 1.0 / (med * med);
+  const double ropz = 1.0 / opz;
+  const double dl = 1.0 / model.inv_dl;
+  const int iv_max = model.n_rest - 2;
+
+  const int grp = lane >> 2, tig = lane & 3;
+  double acc[6][2];  // blocks (0,0) (1,0) (1,1) (2,0) (2,1) (2,2)
+#pragma unroll
+  for (int b = 0; b < 6; ++b) acc[b][0] = acc[b][1] = 0.0;
+  LogProd vprod;
+  int n_sel = 0;
+
+  // per-pixel record of chunk starting at c0 -> rec[lane] = {offset, sqrt weight, weighted flux, table row}
+  auto produce = [&](int c0, double* rec) {
+    const int p = c0 + lane;
+    const int pc = min(p, n_raw - 1);
+    const bool sel = p < whi && !sp.mask[pc];
+    const double x = X[pc] * ropz;
+    int iv = (int)((x - model.rest0) * model.inv_dl);
+    iv = max(0, min(iv, iv_max));
+    const double xo = fma(-(double)iv, dl, x - model.rest0);
+    const double vn = sp.V[pc] * invmed2;
+    double sw = zq_rsqrt(vn);
+    double ys = (sp.Y[pc] * invmed) * sw;
+    if (!sel) { sw = 0.0; ys = 0.0; }
+    vprod.mul(sel ? vn : 1.0);
+    n_sel += sel ? 1 : 0;
+    double4 v;
+    v.x = xo; v.y = sw; v.z = ys; v.w = __longlong_as_double((long long)iv);
+    reinterpret_cast<double4*>(rec)[lane] = v;
+  };
+  // LOAD LAYOUT: lane L = 8 pg + j reads, for pixel pg of the step, the (value, slope) pairs of columns j, j + 8, j + 16 -
+  // the 8 lanes of a pixel cover 128 contiguous bytes per instruction, 4 L1 wavefronts per LDG.128 (round 2, first
+  // version: the DMMA fragment layout itself, lane = 4 grp + tig, put 4 different table rows into every quarter-warp:
+  // 16 wavefronts per LDG.128, l1tex__data_pipe_lsu_wavefronts at 95 % of peak and the tensor pipe at 38 %).
+  // The operands are formed in this layout and moved to the fragment layout (pixel = tig, columns grp + 8 c) by three
+  // 64-bit shuffles with the fixed lane transpose src = 8 tig + grp.
+  const int pg = lane >> 3, lj = lane & 7;
+  const int frag_src = tig * 8 + grp;
+  const bool owns_residual = lj == 4;  // column 16 + 4 = 20 carries -mu: m' = (y - mu) sqrt(1/v)
+  const double2* MS2 = reinterpret_cast<const double2*>(model.MS) + lj;
+  auto load_pairs = [&](const double4& rc, double2& q0, double2& q1, double2& q2) {
+    const double2* row = MS2 + (size_t)__double_as_longlong(rc.w) * ZQ_STRIDE;
+    q0 = __ldg(row);
+    q1 = __ldg(row + 8);
+    q2 = __ldg(row + 16);
+  };
+  auto to_fragment = [&](double& v0, double& v1, double& v2) {
+    v0 = __shfl_sync(0xffffffffu, v0, frag_src);
+    v1 = __shfl_sync(0xffffffffu, v1, frag_src);
+    v2 = __shfl_sync(0xffffffffu, v2, frag_src);
+  };
+
+  // Three-stage software pipeline over the 4-pixel steps g = 8 c + kb:
+  //   step g :  LDG (value, slope) pairs of step g + 2   (its record was read from shared memory during step g - 1)
+  //             LDS record of step g + 3
+  //             6 DMMAs of step g, with the 3 FMA + 3 MUL/FMA that form the operands of step g + 1 between them,
+  //             then the transpose of those operands to the fragment layout
+  // so every load has a whole step - and the other warps' steps - to land before its consumer issues.
+  const int nchunks = whi > wlo ? (whi - wlo + 31) >> 5 : 0;
+  if (nchunks > 0) {
+    double* rec0 = buf;
+    double* rec1 = buf + 32 * ZQ2_REC;
+    produce(wlo, rec0);
+    __syncwarp();
+    double4 ra = reinterpret_cast<const double4*>(rec0)[pg];        // record of step 0
+    double2 qa0, qa1, qa2, qb0, qb1, qb2;
+    load_pairs(ra, qa0, qa1, qa2);
+    double m0 = fma(qa0.y, ra.x, qa0.x) * ra.y;
+    double m1 = fma(qa1.y, ra.x, qa1.x) * ra.y;
+    double m2 = fma(fma(qa2.y, ra.x, qa2.x), ra.y, owns_residual ? ra.z : 0.0);
+    to_fragment(m0, m1, m2);
+    ra = reinterpret_cast<const double4*>(rec0)[4 + pg];            // record of step 1, its pairs
+    load_pairs(ra, qa0, qa1, qa2);
+    double4 rb = reinterpret_cast<const double4*>(rec0)[8 + pg];    // record of step 2 (pairs loaded in step 0)
+    for (int c = 0; c < nchunks; ++c) {
+      double* cur = (c & 1) ? rec1 : rec0;
+      double* nxt = (c & 1) ? rec0 : rec1;
+      if ((c & 7) == 7) vprod.renorm();
+#pragma unroll
+      for (int kb = 0; kb < 8; ++kb) {
+        if (kb == 0) __syncwarp();                      // every lane has read its last record of chunk c - 1 from `nxt`
+        if (kb == 1) produce(wlo + (c + 1) * 32, nxt);  // past the end: zero-weight records, never multiplied in
+        if (kb == 4) __syncwarp();                      // records of chunk c + 1 visible before step kb = 5 reads them
+        load_pairs(rb, qb0, qb1, qb2);                  // pairs of step g + 2
+        const double4 rc = kb + 3 < 8 ? reinterpret_cast<const double4*>(cur)[(kb + 3) * 4 + pg]
+                                      : reinterpret_cast<const double4*>(nxt)[(kb + 3 - 8) * 4 + pg];
+        const double zadd = owns_residual ? ra.z : 0.0;
+        zq_dmma_pinned(acc[0][0], acc[0][1], m0, m0);
+        const double t0 = zq_fma_pinned(qa0.y, ra.x, qa0.x);
+        zq_dmma_pinned(acc[1][0], acc[1][1], m1, m0);
+        const double t1 = zq_fma_pinned(qa1.y, ra.x, qa1.x);
+        zq_dmma_pinned(acc[2][0], acc[2][1], m1, m1);
+        const double t2 = zq_fma_pinned(qa2.y, ra.x, qa2.x);
+        zq_dmma_pinned(acc[3][0], acc[3][1], m2, m0);
+        double n0 = zq_mul_pinned(t0, ra.y);
+        zq_dmma_pinned(acc[4][0], acc[4][1], m2, m1);
+        double n1 = zq_mul_pinned(t1, ra.y);
+        zq_dmma_pinned(acc[5][0], acc[5][1], m2, m2);
+        double n2 = zq_fma_pinned(t2, ra.y, zadd);
+        to_fragment(n0, n1, n2);
+        m0 = n0; m1 = n1; m2 = n2;
+        qa0 = qb0; qa1 = qb1; qa2 = qb2;
+        ra = rb;
+        rb = rc;
+      }
+    }
+  }
+  double lv = vprod.value();
+  if (!(vprod.prod > 0.0)) lv = __longlong_as_double(0x7ff8000000000000LL);  // zero / negative / NaN variance: poison, never +inf
+  const double sum_log_v = warp_sum(lv);
+  const int n_in = (int)(warp_sum((double)n_sel) + 0.5);
+
+  // ---- fragments -> T (24 x 24, lower blocks) -> one row per lane ------------------------------------------------
+  __syncwarp();
+  double* T = buf;
+  {
+    const int bi_of[6] = {0, 1, 1, 2, 2, 2}, bj_of[6] = {0, 0, 1, 0, 1, 2};
+#pragma unroll
+    for (int b = 0; b < 6; ++b) {
+      const int row = bi_of[b] * 8 + grp, col = bj_of[b] * 8 + tig * 2;
+      T[row * ZQ_TSTRIDE + col] = acc[b][0];
+      T[row * ZQ_TSTRIDE + col + 1] = acc[b][1];
+    }
+  }
+  __syncwarp();
+  // Cholesky of the bordered matrix [[B, c], [c', q]] in registers: lane i owns row i (0..20; row 20 = [c', q]).
+  // Right-looking: column j is scaled by 1/sqrt(pivot), then every row subtracts l_ij l_kj from its entries k > j;
+  // after the 20 columns entry (20, 20) is q - z'z (null_gp.py:345-358).  Lanes > 20 compute on zeros.
+  double row[ZQ_K + 1];
+#pragma unroll
+  for (int k = 0; k <= ZQ_K; ++k) {
+    double v = (lane <= ZQ_K && k <= lane) ? T[lane * ZQ_TSTRIDE + k] : 0.0;
+    if (k == lane && k < ZQ_K) v += 1.0;  // + I (null_gp.py:341); row 20 is the projection row
+    row[k] = v;
+  }
+  LogProd pivots;
+#pragma unroll
+  for (int j = 0; j < ZQ_K; ++j) {
+    const double piv = __shfl_sync(0xffffffffu, row[j], j);
+    pivots.mul(piv);
+    if ((j & 3) == 3) pivots.renorm();
+    const double inv = zq_rsqrt(piv);
+    const double l = row[j] * inv;
+    row[j] = l;
+#pragma unroll
+    for (int k = j + 1; k <= ZQ_K; ++k) {
+      const double lk = __shfl_sync(0xffffffffu, l, k);
+      row[k] = fma(-l, lk, row[k]);
+    }
+  }
+  const double quad = __shfl_sync(0xffffffffu, row[ZQ_K], ZQ_K);  // q - z'z
+  double lp = pivots.value();
+  if (!(pivots.prod > 0.0)) lp = __longlong_as_double(0x7ff8000000000000LL);
+  const double ll_window = -0.5 * (quad + (sum_log_v + lp) + (double)n_in * ZQ_LOG_2PI);
+
+  // ---- i.i.d. Gaussians bluewards and redwards of the window (:160-166, :198-210, :252-278) -----------------
+  double side_ll[2];
+#pragma unroll
+  for (int side = 0; side < 2; ++side) {
+    const int begin = side == 0 ? 0 : w.rw_begin, end = side == 0 ? w.bw_end : n_raw;
+    const double m_side = side == 0 ? model.bluewards_mu : model.redwards_mu;
+    const double var_side = side == 0 ? model.bluewards_var : model.redwards_var;
+    double qs = 0.0;
+    LogProd dprod;
+    int cnt = 0, it = 0;
+    for (int p = begin + lane; p < end; p += 32, ++it) {
+      if (!sp.mask[p]) {
+        const double t = fma(sp.Y[p], invmed, -m_side);
+        const double dd = fma(sp.V[p], invmed2, var_side);
+        qs = fma(t * t, zq_rcp(dd), qs);
+        dprod.mul(dd);
+        ++cnt;
+      }
+      if ((it & 7) == 7) dprod.renorm();
+    }
+    double ld = dprod.value();
+    if (!(dprod.prod > 0.0)) ld = __longlong_as_double(0x7ff8000000000000LL);
+    const double q_tot = warp_sum(qs), ld_tot = warp_sum(ld);
+    const int c_tot = (int)(warp_sum((double)cnt) + 0.5);
+    side_ll[side] = -0.5 * (q_tot + ld_tot + (double)c_tot * ZQ_LOG_2PI);
+  }
+  if (lane == 0) out[(size_t)blockIdx.y * S + s] = ll_window + side_ll[0] + side_ll[1];
 }
 
 // np.nanargmax over the samples of each spectrum (first maximum wins); -1 when every sample is NaN

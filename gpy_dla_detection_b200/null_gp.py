@@ -66,17 +66,29 @@ class NullGP:
 
         assert self.M.shape == (self.rest_wavelengths.shape[0], self.params.k)
 
-        ptr = ctypes.c_void_p()
-        _lib.check(
-            _lib.load_library().dla_model_create(
-                _lib.dptr(self.rest_wavelengths), _lib.dptr(self.mu), _lib.dptr(self.M), _lib.dptr(self.log_omega),
-                self.rest_wavelengths.shape[0], self.M.shape[1], self.log_c_0, self.log_tau_0, self.log_beta,
-                self.prev_tau_0, self.prev_beta, ctypes.byref(ptr),
-            )
-        )
-        self._model = _Handle(ptr, "dla_model_destroy")
+        self._model_handle()
         self._spectrum = None
         self.broadening = True
+
+    def _model_handle(self) -> "_Handle":
+        """
+        The learned model on the device, uploaded on first use.  (Lazy so that the methods of this class can be
+        installed on objects built by the REFERENCE's constructors - interop.patch_reference.)
+        """
+        h = self.__dict__.get("_model")
+        if h is None:
+            rest, mu = _lib.f64(self.rest_wavelengths), _lib.f64(self.mu)
+            M, lo = _lib.f64(self.M), _lib.f64(self.log_omega)
+            ptr = ctypes.c_void_p()
+            _lib.check(
+                _lib.load_library().dla_model_create(
+                    _lib.dptr(rest), _lib.dptr(mu), _lib.dptr(M), _lib.dptr(lo), rest.shape[0], M.shape[1],
+                    float(self.log_c_0), float(self.log_tau_0), float(self.log_beta), float(self.prev_tau_0),
+                    float(self.prev_beta), ctypes.byref(ptr),
+                )
+            )
+            h = self._model = _Handle(ptr, "dla_model_destroy")
+        return h
 
     # -- device-side preparation ---------------------------------------------------------------
     def _params_struct(self) -> "_lib.DLAParamsStruct":
@@ -115,7 +127,7 @@ class NullGP:
         ps = self._params_struct()
         _lib.check(
             _lib.load_library().dla_spectrum_create(
-                self._model.ptr, ctypes.byref(ps), _lib.dptr(X), _lib.dptr(Y), _lib.dptr(V), _lib.bptr(mask),
+                self._model_handle().ptr, ctypes.byref(ps), _lib.dptr(X), _lib.dptr(Y), _lib.dptr(V), _lib.bptr(mask),
                 X.shape[0], float(z_qso), 1 if normalize else 0, ctypes.byref(ptr),
             )
         )
@@ -153,12 +165,48 @@ class NullGP:
 
     def get_interp(self, x: np.ndarray, y: np.ndarray, wavelengths: np.ndarray, z_qso: float) -> None:
         """
-        (null_gp.py:179-242) The interpolated, mean-flux-suppressed model is built on the
-        device by `set_data`; calling this again with the object's own (x, wavelengths) is a
-        no-op kept for API parity.
+        Build and interpolate the GP model onto the given pixels (null_gp.py:179-242): x rest wavelengths,
+        wavelengths observed (y is unused, as in the reference).  Sets `this_mu`, `this_M`, `this_omega2`.
+        `set_data(build_model=True)` already does this for the loaded spectrum inside its own kernel; called
+        with any other grid (or after `build_model=False`) the interpolation runs through `dla_model_interp`,
+        and - when the grid has the loaded spectrum's length - the device copy the likelihoods use is rebuilt
+        from the new arrays, so the evidences follow the attributes exactly as they do in the reference.
         """
-        if not (np.array_equal(x, self.x) and np.array_equal(wavelengths, self.this_wavelengths)):
-            raise NotImplementedError("get_interp on a grid other than the one loaded by set_data")
+        x, wl = _lib.f64(x), _lib.f64(wavelengths)
+        assert x.shape == wl.shape and x.ndim == 1
+        if x.shape[0] and (np.min(x) < self.rest_wavelengths[0] or np.max(x) > self.rest_wavelengths[-1]):
+            # scipy.interpolate.interp1d raises for out-of-range x (null_gp.py:67-71)
+            raise ValueError("A value in x_new is outside the interpolation range.")
+        n, k = x.shape[0], self.params.k
+        mu, M, om = np.empty(n), np.empty((n, k)), np.empty(n)
+        _lib.check(
+            _lib.load_library().dla_model_interp(
+                self._model_handle().ptr, int(self.params.num_forest_lines), _lib.dptr(x), _lib.dptr(wl), n, float(z_qso),
+                _lib.dptr(mu), _lib.dptr(M), _lib.dptr(om),
+            )
+        )
+        same = (getattr(self, "this_mu", None) is not None and self.this_mu.shape == mu.shape
+                and np.array_equal(self.this_mu, mu) and np.array_equal(self.this_omega2, om)
+                and np.array_equal(self.this_M, M))
+        self.this_mu, self.this_M, self.this_omega2 = mu, M, om
+        if not same and getattr(self, "_spectrum", None) is not None and hasattr(self, "y") and n == self.y.shape[0]:
+            self._rebuild_prepared()
+
+    def _rebuild_prepared(self) -> None:
+        """Device spectrum from the object's own attributes (y, v, this_mu, this_M, this_omega2, grids, mask)."""
+        broadening = bool(getattr(self, "broadening", True))
+        wl = _lib.f64(self.padded_wavelengths if broadening else self.unmasked_wavelengths)
+        keep = _lib.u8(~self.pixel_mask[self.ind_unmasked])
+        y, v = _lib.f64(self.y), _lib.f64(self.v)
+        mu, M, om = _lib.f64(self.this_mu), _lib.f64(self.this_M), _lib.f64(self.this_omega2)
+        ptr = ctypes.c_void_p()
+        _lib.check(
+            _lib.load_library().dla_spectrum_create_prepared(
+                _lib.dptr(y), _lib.dptr(v), _lib.dptr(mu), _lib.dptr(M), _lib.dptr(om), y.shape[0], M.shape[1],
+                _lib.dptr(wl), wl.shape[0], _lib.bptr(keep), keep.shape[0], 1 if broadening else 0, ctypes.byref(ptr),
+            )
+        )
+        self._spectrum = _Handle(ptr, "dla_spectrum_destroy")
 
     # -- properties of the reference ---------------------------------------------------------------
     mean = property(lambda self: self.mu)

@@ -30,10 +30,13 @@ from . import _tables as tables
 # ----------------------------------------------------------------------------------------
 # learned GP model
 # ----------------------------------------------------------------------------------------
-def make_learned_model(seed: int = 0, k: int = 20) -> Dict[str, np.ndarray]:
-    """Synthetic stand-in for the learned null-model file."""
+def make_learned_model(seed: int = 0, k: int = 20, rest_min: float = 911.75, rest_max: float = 1215.75) -> Dict[str, np.ndarray]:
+    """
+    Synthetic stand-in for the learned null-model file: grid rest_min:0.25:rest_max.  The defaults are
+    the published DLA model's range; examples/gp_find_lls.py:102 trains on 850.75-1420.75 A.
+    """
     rng = np.random.default_rng(seed)
-    rest_wavelengths = 911.75 + 0.25 * np.arange(1217)
+    rest_wavelengths = rest_min + 0.25 * np.arange(int(round((rest_max - rest_min) / 0.25)) + 1)
 
     def bump(center, width, height):
         return height * np.exp(-0.5 * ((rest_wavelengths - center) / width) ** 2)
@@ -127,6 +130,13 @@ def make_subdla_sample_arrays(params: Parameters, num_samples: int = None) -> Di
         Z_lls=Z_lls,
         extrapolate_min_log_nhi=lo,
     )
+
+
+def make_lls_sample_arrays(num_samples: int, min_log_nhi: float = 17.0, max_log_nhi: float = 21.0) -> Dict[str, np.ndarray]:
+    """Absorber samples for the Lyman-limit-system variant (examples/gp_find_lls.py:227-294): uniform in log N_HI."""
+    offsets = halton(num_samples, 2)
+    log_nhi = min_log_nhi + (max_log_nhi - min_log_nhi) * halton(num_samples, 3)
+    return dict(offset_samples=offsets, log_nhi_samples=log_nhi, nhi_samples=10.0**log_nhi)
 
 
 class SyntheticPrior:

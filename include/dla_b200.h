@@ -14,7 +14,10 @@
  *   - return value: 0 = ok, non-zero = error (dla_last_error() gives the text).  NaNs are
  *     in-band results exactly where the reference produces them (dla_gp.py:200-206).
  *   - no CPU fallback: every call fails if no CUDA device is usable.
- *   - one host thread per device; calls on one handle are stream-ordered.
+ *   - threading: the library keeps ONE runtime per process (device, stream, copy stream): one host thread per
+ *     process, one process per GPU (torchrun).  Calls are not re-entrant; calls on one handle are stream-ordered.
+ *     Every handle records the device it was created on and every call checks it against the device selected by
+ *     dla_init, so a handle used after dla_init(another device) fails instead of touching foreign memory.
  */
 #ifndef DLA_B200_H
 #define DLA_B200_H
@@ -76,6 +79,13 @@ int dla_model_create(const double* rest_wavelengths, const double* mu, const dou
                      double log_tau_0, double log_beta, double prev_tau_0, double prev_beta,
                      dla_model** out);
 int dla_model_destroy(dla_model* model);
+
+/* NullGP.get_interp (null_gp.py:179-242) for caller-supplied pixels: x = rest wavelengths (must lie inside the
+ * model grid, as scipy interp1d requires), wavelengths = observed, both (n).  Outputs this_mu (n), this_M (n, k)
+ * row-major, this_omega2 (n): interpolated model with the Kim et al. mean-flux suppression applied. */
+int dla_model_interp(const dla_model* model, int num_forest_lines, const double* x,
+                     const double* wavelengths, int n, double z_qso, double* this_mu, double* this_M,
+                     double* this_omega2);
 
 /* pipeline parameters read by the path (set_parameters.py:21-102) */
 typedef struct dla_params {
@@ -217,6 +227,10 @@ int dla_zqso_inference(const dla_zqso_model* model, const dla_zqso_params* param
 /* timing of the last dla_zqso_inference call (CUDA events on the library stream): the kernels alone, i.e. with the
  * spectra already resident in HBM, and the whole call including the host <-> device copies */
 int dla_zqso_last_timing(double* kernel_ms, double* total_ms);
+/* Testing hook: dla_zqso_inference picks its kernel by the model grid (uniform spacing: median pass +
+ * zqso_likelihood_kernel_v2; otherwise the generic kernel).  on != 0 forces the generic kernel for every model so
+ * that both can be checked on the same inputs. */
+int dla_zqso_force_generic_kernel(int on);
 /* ZGP.set_data + get_interp at one redshift (zqso_gp.py:66-182), element-wise over the n_raw pixels:
  * x = X / (1 + z), normalised flux / variance, interpolated mu (n_raw) and M (n_raw, k) where cls == 1,
  * cls (0 none, 1 modelled, 2 bluewards, 3 redwards), in_window (the first `ind` of :132), this_median.

@@ -268,8 +268,28 @@ def golden_lls():
     ev = gp.log_model_evidences(3)
     out.update(S=S, z_qso=z_q, seed=seed, log_evidences=ev, sample_log_likelihoods=gp.sample_log_likelihoods,
                base_sample_inds=gp.base_sample_inds)
+    # the extended model of examples/gp_find_lls.py:102,162-170: rest grid 850.75-1420.75 A (bluewards of the Lyman limit,
+    # redwards of Ly-alpha), normalisation window 1425-1475 A, absorbers from log N = 17
+    grid_kw = dict(min_lambda=850.75, max_lambda=1420.75, normalization_min_lambda=1425.0, normalization_max_lambda=1475.0)
+    S2, z_q2, seed2 = 96, 3.9, 23
+    rp2 = RParameters(num_dla_samples=S2, num_lines=4, **grid_kw)
+    p2 = Parameters(num_dla_samples=S2, num_lines=4, **grid_kw)
+    model2 = synthetic.make_learned_model(1, rest_min=850.75, rest_max=1420.75)
+    prior2 = synthetic.SyntheticPrior(p2)
+    lls2 = synthetic.make_lls_sample_arrays(S2)
+    wl2, fl2, nv2, pm2 = synthetic.make_spectrum(model2, z_q2, seed=seed2, params=p2)
+    margs2 = (model2["rest_wavelengths"], model2["mu"], model2["M"], model2["log_omega"], model2["log_c_0"],
+              model2["log_tau_0"], model2["log_beta"])
+    gp2 = RLLSGP(rp2, prior2, ref_loader.RefDLASamples(rp2, lls2), *margs2)
+    gp2.set_data(rp2.emitted_wavelengths(wl2, z_q2), fl2, nv2, pm2, z_q2, build_model=True)
+    np.random.seed(0)
+    ev2 = gp2.log_model_evidences(2)
+    out.update(ext_S=S2, ext_z_qso=z_q2, ext_seed=seed2, ext_log_evidences=ev2,
+               ext_sample_log_likelihoods=gp2.sample_log_likelihoods, ext_base_sample_inds=gp2.base_sample_inds,
+               ext_this_mu=gp2.this_mu, ext_this_omega2=gp2.this_omega2, ext_ind=gp2.ind, ext_x=gp2.x,
+               ext_normalization_median=gp2.normalization_median)
     np.savez_compressed(os.path.join(HERE, "lls_golden.npz"), **out)
-    print("lls_golden.npz written", ev)
+    print("lls_golden.npz written", ev, ev2, "n =", gp2.x.shape[0])
 
 
 # 20 of the 128 spectra tools/parity_sweep.py runs: every 8th, plus the four highest redshifts of the draw

@@ -46,3 +46,35 @@ def test_lls_gp_evidences_golden(gpu):
     assert np.max(np.abs(ev - g["log_evidences"])) < 1e-6
     assert H.ll_err(gp.sample_log_likelihoods, g["sample_log_likelihoods"]) < 1e-9
     assert np.array_equal(gp.base_sample_inds, g["base_sample_inds"])
+
+
+def test_lls_extended_model_grid_golden(gpu):
+    """
+    The model range of examples/gp_find_lls.py:102,162-170: rest grid 850.75-1420.75 A (2 281 points), normalisation
+    window 1425-1475 A, num_lines = 4, absorbers from log N = 17; n = 2 194 modelled pixels (the DLA range has <= 1 250).
+    """
+    from gpy_dla_detection_b200.dla_samples import DLASamplesArrays
+    from gpy_dla_detection_b200.lls_gp import LLSGP
+    from gpy_dla_detection_b200.set_parameters import Parameters
+
+    g = H.golden("lls_golden.npz")
+    S, z_qso = int(g["ext_S"]), float(g["ext_z_qso"])
+    p = Parameters(num_dla_samples=S, num_lines=4, min_lambda=850.75, max_lambda=1420.75,
+                   normalization_min_lambda=1425.0, normalization_max_lambda=1475.0)
+    model = synthetic.make_learned_model(1, rest_min=850.75, rest_max=1420.75)
+    assert model["rest_wavelengths"].shape == (2281,) and model["rest_wavelengths"][-1] == 1420.75
+    prior = synthetic.SyntheticPrior(p)
+    lls = synthetic.make_lls_sample_arrays(S)
+    wl, fl, nv, pm = synthetic.make_spectrum(model, z_qso, seed=int(g["ext_seed"]), params=p)
+    d = DLASamplesArrays(p, prior, lls["offset_samples"], lls["log_nhi_samples"], lls["nhi_samples"])
+    gp = LLSGP(p, prior, d, *H.model_args(model))
+    gp.set_data(wl / (1 + z_qso), fl, nv, pm, z_qso, build_model=True)
+    assert np.array_equal(gp.ind, g["ext_ind"]) and np.array_equal(gp.x, g["ext_x"])
+    assert gp.normalization_median == float(g["ext_normalization_median"])
+    assert np.max(np.abs(gp.this_mu - g["ext_this_mu"])) < 1e-13
+    assert np.max(np.abs(gp.this_omega2 / g["ext_this_omega2"] - 1)) < 1e-12
+    np.random.seed(0)
+    ev = gp.log_model_evidences(2)
+    assert np.max(np.abs(ev - g["ext_log_evidences"])) < 1e-6
+    assert H.ll_err(gp.sample_log_likelihoods, g["ext_sample_log_likelihoods"]) < 1e-9
+    assert np.array_equal(gp.base_sample_inds, g["ext_base_sample_inds"])

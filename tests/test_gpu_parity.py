@@ -599,3 +599,45 @@ def test_catalogue_repeats_are_bit_identical(gpu):
             continue
         for k, v in first.items():
             assert np.array_equal(v, arrays[k], equal_nan=True), k
+
+
+def test_unnormalised_flux_known_answers(gpu, O):
+    """
+    ADVICE r1: the log-determinant is a log of exponent-renormalised products, which must stay finite where the
+    reference (a sum of logs) does: noise variance ~ 1e-30 (20 pivots of ~1e31: their plain product overflows),
+    ~ 1e+30, and a consistent rescaling of flux and model by 1e+-15.
+    """
+    import ctypes
+
+    from gpy_dla_detection_b200.log_posterior_mcmc import _Prepared
+
+    rng = np.random.default_rng(5)
+    n, k = 700, 20
+    M = 0.1 * rng.standard_normal((n, k))
+    mu = 1.0 + 0.1 * rng.standard_normal(n)
+    y = mu + M @ rng.standard_normal(k) + 0.05 * rng.standard_normal(n)
+    om2 = 0.01 * (1.0 + rng.random(n))
+    wl = 10 ** (3.6 + 1e-4 * np.arange(n + 6))
+    mask, ind_unmasked = np.zeros(n, dtype=bool), np.ones(n, dtype=bool)
+    lib = gpu.load_library()
+
+    def null_evidence(y_, v_, mu_, M_, om2_):
+        prep = _Prepared(y_, v_, wl, mu_, M_, om2_, mask, ind_unmasked)
+        out = ctypes.c_double()
+        gpu.check(lib.dla_null_log_model_evidence(prep.handle.ptr, ctypes.byref(out)))
+        return out.value
+
+    cases = [
+        ("v=1e-30", y, np.full(n, 1e-30), mu, M, np.zeros(n)),
+        ("v=1e+30", y, np.full(n, 1e30), mu, M, om2),
+        ("scale 1e-15", y * 1e-15, np.full(n, 0.04) * 1e-30, mu * 1e-15, M * 1e-15, om2 * 1e-30),
+        ("scale 1e+15", y * 1e15, np.full(n, 0.04) * 1e30, mu * 1e15, M * 1e15, om2 * 1e30),
+    ]
+    for name, y_, v_, mu_, M_, om2_ in cases:
+        ref = O.log_mvnpdf_low_rank(y_, mu_, M_, om2_ + v_)
+        got = null_evidence(y_, v_, mu_, M_, om2_)
+        assert np.isfinite(ref) and np.isfinite(got), name
+        assert abs(got - ref) < 1e-9 * max(abs(ref), 1.0), (name, got, ref)
+    # a zero variance makes d = 0: the reference's log(0) / division by zero gives nan or -inf, never +inf
+    bad = null_evidence(y, np.zeros(n), mu, M, np.zeros(n))
+    assert not (bad == np.inf)

@@ -121,3 +121,41 @@ def test_unsorted_wavelengths_are_rejected(gpu):
     wl, fl, nv, pm = synthetic.make_zqso_spectrum(model, 3.0, seed=1)
     with pytest.raises(gpu.DLALibraryError, match="increasing"):
         gp.inference_z_qsos([(wl[::-1].copy(), fl, nv, pm)], np.array([3.0]))
+
+
+def test_generic_kernel_and_uniform_grid_kernel_agree(gpu):
+    """
+    dla_zqso_inference picks zqso_likelihood_kernel_v2 (+ the median pass) for a uniform model grid and the generic
+    kernel otherwise: both on the same inputs - a dense sweep (neighbouring samples share the sorted normalisation
+    window) and a coarse one (one sort per sample in the median pass).
+    """
+    lib = gpu.load_library()
+    model, gp = build_zgp(512)
+    spectra = [synthetic.make_zqso_spectrum(model, z, seed=80 + i) for i, z in enumerate((2.3, 3.9, 5.2))]
+    spectra[1] = tuple(a[250:4400] for a in spectra[1])
+    for zs in (np.linspace(2.14, 6.16, 10000)[3000:3512], np.linspace(2.14, 6.16, 37)):
+        fast = gp.inference_z_qsos(spectra, zs)
+        try:
+            gpu.check(lib.dla_zqso_force_generic_kernel(1))
+            slow = gp.inference_z_qsos(spectra, zs)
+        finally:
+            gpu.check(lib.dla_zqso_force_generic_kernel(0))
+        assert np.array_equal(np.isnan(fast["sample_log_likelihoods"]), np.isnan(slow["sample_log_likelihoods"]))
+        assert H.ll_err(fast["sample_log_likelihoods"], slow["sample_log_likelihoods"]) < 1e-10
+        assert np.array_equal(fast["map_index"], slow["map_index"])
+
+
+def test_flux_scale_invariance(gpu):
+    """
+    ZGP normalises every spectrum by its own median, so flux in units of 1e-30 or 1e+30 must give the same sample
+    likelihoods (products of variances / pivots must not overflow or underflow into +-inf).
+    """
+    model, gp = build_zgp(64)
+    wl, fl, nv, pm = synthetic.make_zqso_spectrum(model, 3.3, seed=9)
+    zs = np.linspace(2.14, 6.16, 64)
+    base = gp.inference_z_qsos([(wl, fl, nv, pm)], zs)["sample_log_likelihoods"][0]
+    assert np.all(np.isfinite(base))
+    for c in (1e-30, 1e30):
+        got = gp.inference_z_qsos([(wl, fl * c, nv * c * c, pm)], zs)["sample_log_likelihoods"][0]
+        assert np.all(np.isfinite(got))
+        assert H.ll_err(got, base) < 1e-9, c

@@ -167,3 +167,31 @@ def test_sharded_catalogue_gather_world_size_2_gloo(tmp_path, Q):
     res = subprocess.run(cmd, capture_output=True, text=True, timeout=240, env=env)
     assert res.returncode == 0, res.stdout[-2000:] + res.stderr[-4000:]
     assert "GATHER_OK %d 2" % Q in res.stdout
+
+
+def test_patch_reference_installs_and_restores():
+    """interop.patch_reference swaps the hot-path methods of the reference's classes and undo() puts them back (no GPU needed)."""
+    from oracle import ref_loader
+
+    if not ref_loader.reference_available():
+        pytest.skip("reference package not present")
+    pkg = ref_loader.load_reference()
+    from gpy_dla_detection import dla_gp as rd, null_gp as rn, subdla_gp as rs, voigt as rv
+
+    from gpy_dla_detection_b200 import interop, null_gp, voigt
+
+    before = {(c, n): c.__dict__.get(n) for c in (rn.NullGP, rd.DLAGP, rs.SubDLAGP)
+              for n in ("set_data", "log_model_evidence", "log_model_evidences", "this_dla_gp", "log_mvnpdf_low_rank")}
+    ref_voigt = rv.voigt_absorption
+    undo = interop.patch_reference(pkg)
+    try:
+        assert rn.NullGP.set_data is null_gp.NullGP.set_data
+        assert isinstance(rn.NullGP.__dict__["log_mvnpdf_low_rank"], staticmethod)
+        assert rd.DLAGP.__dict__["log_model_evidences"] is not before[(rd.DLAGP, "log_model_evidences")]
+        assert rv.voigt_absorption is voigt.voigt_absorption and rd.voigt_absorption is voigt.voigt_absorption
+        assert issubclass(rd.DLAGP, rn.NullGP)  # the reference's hierarchy is untouched: its isinstance checks hold
+    finally:
+        undo()
+    for (c, n), old in before.items():
+        assert c.__dict__.get(n) is old, (c, n)
+    assert rv.voigt_absorption is ref_voigt and rd.voigt_absorption is ref_voigt
