@@ -953,12 +953,19 @@ extern "C" int dla_resample_indices(const double* W, const double* uniforms, int
   DLA_CHECK_READY();
   Runtime& rt = runtime();
   DLA_REQUIRE(W && uniforms && out && S >= 1, "bad argument");
-  DevBuf<double> dW, dU, scratch;
-  DevBuf<int32_t> dout;
-  DLA_CUDA(dW.alloc(S));
-  DLA_CUDA(dU.alloc(S));
-  DLA_CUDA(scratch.alloc(S));
-  DLA_CUDA(dout.alloc(S));
+  // scratch kept between calls (the class API calls this once per level per spectrum; four cudaMalloc / cudaFree pairs
+  // per call each synchronised the device); re-created when dla_init moves the library to another device
+  static DevBuf<double> dW, dU, scratch;
+  static DevBuf<int32_t> dout;
+  static int scratch_device = -1;
+  if (scratch_device != rt.device) {
+    dW.release(); dU.release(); scratch.release(); dout.release();
+    scratch_device = rt.device;
+  }
+  DLA_CUDA(dW.ensure(S));
+  DLA_CUDA(dU.ensure(S));
+  DLA_CUDA(scratch.ensure(S));
+  DLA_CUDA(dout.ensure(S));
   DLA_CUDA(dW.upload(W, S, rt.stream));
   DLA_CUDA(dU.upload(uniforms, S, rt.stream));
   resample_kernel<<<1, 1024, 0, rt.stream>>>(dW.p, dU.p, S, scratch.p, dout.p);

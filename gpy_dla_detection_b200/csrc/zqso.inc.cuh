@@ -5,6 +5,13 @@ struct dla_zqso_model {
   DevBuf<double> rest, mu, mu_slope, M, M_slope, MS;
   ZqsoModelDev dev;
   int device = -1;
+  // workspace of dla_zqso_inference, kept between calls (a cudaMalloc / cudaFree pair per call synchronises the device)
+  struct Workspace {
+    DevBuf<double> X, Y, V, z, ll, zmap, med;
+    DevBuf<uint8_t> mask;
+    DevBuf<int32_t> mapi;
+    DevBuf<ZqsoSpectrum> desc;
+  } ws;
 };
 
 // timing of the last dla_zqso_inference call: kernels only (inputs resident) and the whole call
@@ -118,29 +125,30 @@ extern "C" int dla_zqso_inference(const dla_zqso_model* model, const dla_zqso_pa
   DLA_CUDA(cudaFuncSetAttribute(zqso_likelihood_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   // uniform model grid (the published one): median pass + the v2 kernel; any other grid: the generic kernel
   const bool v2 = model->dev.uniform != 0 && g_zqso_force_generic == 0;
-  const size_t smem_v2 = (size_t)ZQ_WARPS * ZQ2_PER_WARP * sizeof(double);
+  const size_t smem_v2 = (size_t)ZQ2_WARPS * ZQ2_PER_WARP * sizeof(double);
   const size_t smem_med = (size_t)norm_cap * (sizeof(double) + sizeof(int));
-  DevBuf<double> dmed;
+  DevBuf<double>& dmed = const_cast<dla_zqso_model*>(model)->ws.med;
 
-  DevBuf<double> dX, dY, dV, dz, dll, dzmap;
-  DevBuf<uint8_t> dmask;
-  DevBuf<int32_t> dmapi;
-  DevBuf<ZqsoSpectrum> ddesc;
-  DLA_CUDA(dX.alloc(total));
-  DLA_CUDA(dY.alloc(total));
-  DLA_CUDA(dV.alloc(total));
-  DLA_CUDA(dmask.alloc(total));
-  DLA_CUDA(dz.alloc(S));
+  dla_zqso_model::Workspace& ws = const_cast<dla_zqso_model*>(model)->ws;
+  DevBuf<double>&dX = ws.X, &dY = ws.Y, &dV = ws.V, &dz = ws.z, &dll = ws.ll, &dzmap = ws.zmap;
+  DevBuf<uint8_t>& dmask = ws.mask;
+  DevBuf<int32_t>& dmapi = ws.mapi;
+  DevBuf<ZqsoSpectrum>& ddesc = ws.desc;
+  DLA_CUDA(dX.ensure(total));
+  DLA_CUDA(dY.ensure(total));
+  DLA_CUDA(dV.ensure(total));
+  DLA_CUDA(dmask.ensure(total));
+  DLA_CUDA(dz.ensure(S));
   DLA_CUDA(dX.upload(wavelengths, total, rt.stream));
   DLA_CUDA(dY.upload(flux, total, rt.stream));
   DLA_CUDA(dV.upload(noise_variance, total, rt.stream));
   DLA_CUDA(dmask.upload(pixel_mask, total, rt.stream));
   DLA_CUDA(dz.upload(z_samples, S, rt.stream));
   const int chunk = std::max(1, std::min(num_spectra, (int)std::min<size_t>(16384, ((size_t)1 << 28) / (size_t)S)));  // <= 2 GiB of ll
-  DLA_CUDA(dll.alloc((size_t)chunk * S));
-  DLA_CUDA(dzmap.alloc(chunk));
-  DLA_CUDA(dmapi.alloc(chunk));
-  DLA_CUDA(ddesc.alloc(chunk));
+  DLA_CUDA(dll.ensure((size_t)chunk * S));
+  DLA_CUDA(dzmap.ensure(chunk));
+  DLA_CUDA(dmapi.ensure(chunk));
+  DLA_CUDA(ddesc.ensure(chunk));
   std::vector<ZqsoSpectrum> h_desc(chunk);
   cudaEvent_t e_k0, e_k1;
   DLA_CUDA(cudaEventCreate(&e_k0));
@@ -166,7 +174,8 @@ extern "C" int dla_zqso_inference(const dla_zqso_model* model, const dla_zqso_pa
       dim3 mgrid((S + ZQ2_ZPB - 1) / ZQ2_ZPB, nb);
       zqso_median_batch_kernel<<<mgrid, 256, smem_med, rt.stream>>>(ddesc.p, dz.p, S, to_zqso_params(params), norm_cap, dmed.p);
       DLA_LAUNCHED();
-      zqso_likelihood_kernel_v2<<<grid, ZQ_WARPS * 32, smem_v2, rt.stream>>>(ddesc.p, dz.p, S, dmed.p, model->dev,
+      dim3 grid2((S + ZQ2_WARPS - 1) / ZQ2_WARPS, nb);
+      zqso_likelihood_kernel_v2<<<grid2, ZQ2_WARPS * 32, smem_v2, rt.stream>>>(ddesc.p, dz.p, S, dmed.p, model->dev,
                                                                             to_zqso_params(params), dll.p);
       DLA_LAUNCHED();
     } else {

@@ -548,17 +548,26 @@ __device__ __forceinline__ double zq_rsqrt(double x) {
   return (x > 1e-290 && x < 1e290) ? y : 1.0 / sqrt(x);
 }
 
-// grid = (ceil(S / 8), num_spectra), block = 256, dynamic smem = 8 * ZQ2_PER_WARP doubles.  Uniform model grid only.
+// grid = (ceil(S / ZQ2_WARPS), num_spectra), block = 32 ZQ2_WARPS, dynamic smem = ZQ2_WARPS * ZQ2_PER_WARP doubles.  Uniform model grid only.
 #ifndef ZQ2_MIN_CTAS
 #define ZQ2_MIN_CTAS 2
 #endif
-__global__ void __launch_bounds__(ZQ_WARPS * 32, ZQ2_MIN_CTAS)
+#ifndef ZQ2_WARPS
+#define ZQ2_WARPS 8
+#endif
+#ifndef ZQ2_PREFETCH_PIX
+#define ZQ2_PREFETCH_PIX 1
+#endif
+#ifndef ZQ2_SCALAR_FIRST
+#define ZQ2_SCALAR_FIRST 0
+#endif
+__global__ void __launch_bounds__(ZQ2_WARPS * 32, ZQ2_MIN_CTAS)
 zqso_likelihood_kernel_v2(const ZqsoSpectrum* __restrict__ spectra, const double* __restrict__ z_samples, int S,
                           const double* __restrict__ med_all, ZqsoModelDev model, ZqsoParamsDev prm,
                           double* __restrict__ out /* [num_spectra][S] */) {
   extern __shared__ double zq_smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int s = blockIdx.x * ZQ_WARPS + warp;
+  const int s = blockIdx.x * ZQ2_WARPS + warp;
   if (s >= S) return;
   const ZqsoSpectrum sp = spectra[blockIdx.y];
   double* buf = zq_smem + (size_t)warp * ZQ2_PER_WARP;
@@ -582,24 +591,40 @@ zqso_likelihood_kernel_v2(const ZqsoSpectrum* __restrict__ spectra, const double
   LogProd vprod;
   int n_sel = 0;
 
-  // per-pixel record of chunk starting at c0 -> rec[lane] = {offset, sqrt weight, weighted flux, table row}
+  // per-pixel record of chunk starting at c0 -> rec[lane] = {offset, sqrt weight, weighted flux, table row}.
+  // The pixel's inputs are fetched one chunk ahead (fetch), so that the arithmetic never waits for a global load
+  // (third version: the loads sat in front of the first DFMA of produce, 12 % of all stall samples).
+  double pX = 0.0, pV = 1.0, pY = 0.0;
+  bool pM = true;
+  auto fetch = [&](int c0) {
+    const int pc = min(c0 + lane, n_raw - 1);
+    pX = X[pc];
+    pV = sp.V[pc];
+    pY = sp.Y[pc];
+    pM = sp.mask[pc] != 0;
+  };
   auto produce = [&](int c0, double* rec) {
+#if !ZQ2_PREFETCH_PIX
+    fetch(c0);
+#endif
     const int p = c0 + lane;
-    const int pc = min(p, n_raw - 1);
-    const bool sel = p < whi && !sp.mask[pc];
-    const double x = X[pc] * ropz;
+    const bool sel = p < whi && !pM;
+    const double x = pX * ropz;
     int iv = (int)((x - model.rest0) * model.inv_dl);
     iv = max(0, min(iv, iv_max));
     const double xo = fma(-(double)iv, dl, x - model.rest0);
-    const double vn = sp.V[pc] * invmed2;
+    const double vn = pV * invmed2;
     double sw = zq_rsqrt(vn);
-    double ys = (sp.Y[pc] * invmed) * sw;
+    double ys = (pY * invmed) * sw;
     if (!sel) { sw = 0.0; ys = 0.0; }
     vprod.mul(sel ? vn : 1.0);
     n_sel += sel ? 1 : 0;
     double4 v;
     v.x = xo; v.y = sw; v.z = ys; v.w = __longlong_as_double((long long)iv);
     reinterpret_cast<double4*>(rec)[lane] = v;
+#if ZQ2_PREFETCH_PIX
+    fetch(c0 + 32);
+#endif
   };
   // LOAD LAYOUT: lane L = 8 pg + j reads, for pixel pg of the step, the (value, slope) pairs of columns j, j + 8, j + 16 -
   // the 8 lanes of a pixel cover 128 contiguous bytes per instruction, 4 L1 wavefronts per LDG.128 (round 2, first
@@ -623,28 +648,43 @@ zqso_likelihood_kernel_v2(const ZqsoSpectrum* __restrict__ spectra, const double
     v2 = __shfl_sync(0xffffffffu, v2, frag_src);
   };
 
-  // Three-stage software pipeline over the 4-pixel steps g = 8 c + kb:
-  //   step g :  LDG (value, slope) pairs of step g + 2   (its record was read from shared memory during step g - 1)
-  //             LDS record of step g + 3
-  //             6 DMMAs of step g, with the 3 FMA + 3 MUL/FMA that form the operands of step g + 1 between them,
-  //             then the transpose of those operands to the fragment layout
-  // so every load has a whole step - and the other warps' steps - to land before its consumer issues.
+  // Four-stage software pipeline over the 4-pixel steps g = 8 c + kb:
+  //   step g :  SHFL  operands of step g + 1 (formed during step g - 1) -> fragment layout: six DMMAs of cover
+  //             LDG   (value, slope) pairs of step g + 3 (its record was read from shared memory during step g - 1)
+  //             LDS   record of step g + 4
+  //             DMMA  x 6 of step g, with the 3 FMA + 3 MUL/FMA that form the operands of step g + 2 between them
+  // so no consumer issues in the step that issued its producer (second version: LDS -> address -> LDG -> FMA inside one
+  // step: long_scoreboard 33 %; third: operands shuffled at the end of the step that uses them next: short_scoreboard
+  // on the first DMMAs).
   const int nchunks = whi > wlo ? (whi - wlo + 31) >> 5 : 0;
   if (nchunks > 0) {
     double* rec0 = buf;
     double* rec1 = buf + 32 * ZQ2_REC;
+#if ZQ2_PREFETCH_PIX
+    fetch(wlo);
+#endif
     produce(wlo, rec0);
     __syncwarp();
-    double4 ra = reinterpret_cast<const double4*>(rec0)[pg];        // record of step 0
+    const double4* r0 = reinterpret_cast<const double4*>(rec0);
     double2 qa0, qa1, qa2, qb0, qb1, qb2;
+    auto form = [&](const double4& rc, const double2& q0, const double2& q1, const double2& q2, double& v0, double& v1,
+                    double& v2) {
+      v0 = fma(q0.y, rc.x, q0.x) * rc.y;
+      v1 = fma(q1.y, rc.x, q1.x) * rc.y;
+      v2 = fma(fma(q2.y, rc.x, q2.x), rc.y, owns_residual ? rc.z : 0.0);
+    };
+    // prologue: fragment operands of step 0, load-layout operands of step 1, pairs of step 2, records of steps 2 and 3
+    double4 ra = r0[pg];
     load_pairs(ra, qa0, qa1, qa2);
-    double m0 = fma(qa0.y, ra.x, qa0.x) * ra.y;
-    double m1 = fma(qa1.y, ra.x, qa1.x) * ra.y;
-    double m2 = fma(fma(qa2.y, ra.x, qa2.x), ra.y, owns_residual ? ra.z : 0.0);
+    double m0, m1, m2, n0, n1, n2;
+    form(ra, qa0, qa1, qa2, m0, m1, m2);
     to_fragment(m0, m1, m2);
-    ra = reinterpret_cast<const double4*>(rec0)[4 + pg];            // record of step 1, its pairs
+    ra = r0[4 + pg];
     load_pairs(ra, qa0, qa1, qa2);
-    double4 rb = reinterpret_cast<const double4*>(rec0)[8 + pg];    // record of step 2 (pairs loaded in step 0)
+    form(ra, qa0, qa1, qa2, n0, n1, n2);
+    ra = r0[8 + pg];                       // record of step 2 and its pairs
+    load_pairs(ra, qa0, qa1, qa2);
+    double4 rb = r0[12 + pg];              // record of step 3 (pairs loaded in step 0)
     for (int c = 0; c < nchunks; ++c) {
       double* cur = (c & 1) ? rec1 : rec0;
       double* nxt = (c & 1) ? rec0 : rec1;
@@ -653,11 +693,27 @@ zqso_likelihood_kernel_v2(const ZqsoSpectrum* __restrict__ spectra, const double
       for (int kb = 0; kb < 8; ++kb) {
         if (kb == 0) __syncwarp();                      // every lane has read its last record of chunk c - 1 from `nxt`
         if (kb == 1) produce(wlo + (c + 1) * 32, nxt);  // past the end: zero-weight records, never multiplied in
-        if (kb == 4) __syncwarp();                      // records of chunk c + 1 visible before step kb = 5 reads them
-        load_pairs(rb, qb0, qb1, qb2);                  // pairs of step g + 2
-        const double4 rc = kb + 3 < 8 ? reinterpret_cast<const double4*>(cur)[(kb + 3) * 4 + pg]
-                                      : reinterpret_cast<const double4*>(nxt)[(kb + 3 - 8) * 4 + pg];
+        if (kb == 3) __syncwarp();                      // records of chunk c + 1 visible before step kb = 4 reads them
+        double f0 = n0, f1 = n1, f2 = n2;
+        to_fragment(f0, f1, f2);                        // operands of step g + 1
+        load_pairs(rb, qb0, qb1, qb2);                  // pairs of step g + 3
+        const double4 rc = kb + 4 < 8 ? reinterpret_cast<const double4*>(cur)[(kb + 4) * 4 + pg]
+                                      : reinterpret_cast<const double4*>(nxt)[(kb + 4 - 8) * 4 + pg];
         const double zadd = owns_residual ? ra.z : 0.0;
+#if ZQ2_SCALAR_FIRST
+        const double t0 = zq_fma_pinned(qa0.y, ra.x, qa0.x);
+        const double t1 = zq_fma_pinned(qa1.y, ra.x, qa1.x);
+        const double t2 = zq_fma_pinned(qa2.y, ra.x, qa2.x);
+        n0 = zq_mul_pinned(t0, ra.y);
+        n1 = zq_mul_pinned(t1, ra.y);
+        n2 = zq_fma_pinned(t2, ra.y, zadd);
+        zq_dmma_pinned(acc[0][0], acc[0][1], m0, m0);
+        zq_dmma_pinned(acc[1][0], acc[1][1], m1, m0);
+        zq_dmma_pinned(acc[2][0], acc[2][1], m1, m1);
+        zq_dmma_pinned(acc[3][0], acc[3][1], m2, m0);
+        zq_dmma_pinned(acc[4][0], acc[4][1], m2, m1);
+        zq_dmma_pinned(acc[5][0], acc[5][1], m2, m2);
+#else
         zq_dmma_pinned(acc[0][0], acc[0][1], m0, m0);
         const double t0 = zq_fma_pinned(qa0.y, ra.x, qa0.x);
         zq_dmma_pinned(acc[1][0], acc[1][1], m1, m0);
@@ -665,13 +721,13 @@ zqso_likelihood_kernel_v2(const ZqsoSpectrum* __restrict__ spectra, const double
         zq_dmma_pinned(acc[2][0], acc[2][1], m1, m1);
         const double t2 = zq_fma_pinned(qa2.y, ra.x, qa2.x);
         zq_dmma_pinned(acc[3][0], acc[3][1], m2, m0);
-        double n0 = zq_mul_pinned(t0, ra.y);
+        n0 = zq_mul_pinned(t0, ra.y);
         zq_dmma_pinned(acc[4][0], acc[4][1], m2, m1);
-        double n1 = zq_mul_pinned(t1, ra.y);
+        n1 = zq_mul_pinned(t1, ra.y);
         zq_dmma_pinned(acc[5][0], acc[5][1], m2, m2);
-        double n2 = zq_fma_pinned(t2, ra.y, zadd);
-        to_fragment(n0, n1, n2);
-        m0 = n0; m1 = n1; m2 = n2;
+        n2 = zq_fma_pinned(t2, ra.y, zadd);
+#endif
+        m0 = f0; m1 = f1; m2 = f2;
         qa0 = qb0; qa1 = qb1; qa2 = qb2;
         ra = rb;
         rb = rc;
