@@ -132,6 +132,7 @@ SIGNATURES = {
         c_int,
         [c_void_p, _dp, _dp, _dp, POINTER(c_longlong), _dp],
     ),
+    "dla_catalogue_last_counts": (c_int, [c_void_p, POINTER(c_longlong), POINTER(c_longlong)]),
     "dla_zqso_model_create": (
         c_int,
         [_dp, _dp, _dp, c_int, c_int, c_double, c_double, c_double, c_double, POINTER(c_void_p)],

@@ -79,6 +79,10 @@ __global__ void init_rows_kernel(int32_t* __restrict__ rows, int S, int nrows, c
 // catalogue of any length streams through (the staged variant keeps the raw catalogue resident instead and
 // only measures the device path).
 // ---------------------------------------------------------------------------------------------------
+// per-spectrum control block on the device: [0] DLA level-loop alive flag, [1] status, [2] usable (constant), [3] pad,
+// [4 + level] samples evaluated at that level (written by compact_level_kernel, read by the likelihood launch)
+constexpr int CAT_ALIVE = 4 + LK_MAX_ROWS;
+
 struct CatSlot {
   // raw spectra of the batch (host source)
   DevBuf<double> wl, flux, var;
@@ -93,7 +97,8 @@ struct CatSlot {
   PinnedBuf<double> h_scalars;          // [B][8]
   PinnedBuf<unsigned char> h_desc;      // all descriptors of compute(i), one block
   PinnedBuf<double> h_res;              // result block of the batch
-  PinnedBuf<int> h_alive;               // [B][4]
+  PinnedBuf<int> h_alive;               // [B][CAT_ALIVE]
+  std::vector<unsigned char> usable_b;  // spectrum had pixels to model (level-0 evaluations ran)
   PinnedBuf<double> h_sample_dla, h_sample_sub;  // optional per-sample arrays
   PinnedBuf<int32_t> h_inds;
   // bookkeeping: (q0, nb) of the batch whose prep is queued; (c_q0, c_nb) of the batch whose compute is queued - the
@@ -136,12 +141,16 @@ struct dla_catalogue {
   DevBuf<double> res;    // [log_priors | log_lik | log_post | model_post] (B x m each), p_dla, p_no_dla (B), map_z, map_lognhi (B x md x md)
   DevBuf<double> basis;  // Gram basis panels of the batch's spectra
   DevBuf<int32_t> rows, inds_t, map_ind;
-  DevBuf<int> alive;  // [B][4] : DLA level-loop alive flag, status, usable (constant), pad
+  // compacted launches of levels >= 1 (compact_level_kernel): per spectrum S entries each
+  DevBuf<int32_t> sel, pos_a, pos_b, rows0_c, rows1_c;
+  DevBuf<double> raw_slots;  // [B][S] raw log-likelihoods of the current level in slot order
+  DevBuf<int> alive;  // [B][CAT_ALIVE] control blocks
   DevBuf<unsigned char> desc;  // device copy of the descriptor block
   cudaEvent_t ev_call0 = nullptr, ev_call1 = nullptr;
   // timing of the last run
   double total_ms = 0, gram_ms = 0, voigt_ms = 0, gram_flops = 0;
   long long launches = 0;
+  long long lk_evaluated = 0, lk_masked = 0;  // likelihood evaluations run / left out by the separation mask
   ~dla_catalogue() {
     if (ev_call0) cudaEventDestroy(ev_call0);
     if (ev_call1) cudaEventDestroy(ev_call1);
@@ -288,7 +297,7 @@ static CatResLayout cat_res_layout(size_t B, size_t m, size_t md) {
 
 // descriptor block of one batch: byte offsets of the typed arrays inside it
 struct CatDescLayout {
-  size_t basis, grid, lk, ev, map, gather, total;
+  size_t basis, grid, lk, ev, map, gather, compact, scatter, total;
 };
 static CatDescLayout cat_desc_layout(size_t B, size_t md) {
   auto up = [](size_t x) { return (x + 255) / 256 * 256; };
@@ -300,6 +309,8 @@ static CatDescLayout cat_desc_layout(size_t B, size_t md) {
   L.ev = o; o = up(o + sizeof(EvidenceLevel) * B * (md + 1));
   L.map = o; o = up(o + sizeof(MapTask) * B);
   L.gather = o; o = up(o + sizeof(GatherTask) * B);
+  L.compact = o; o = up(o + sizeof(CompactTask) * B * md);
+  L.scatter = o; o = up(o + sizeof(ScatterTask) * B);
   L.total = o;
   return L;
 }
@@ -334,7 +345,7 @@ static int cat_ensure_workspace(dla_catalogue* cat, size_t cap, bool host_source
     DLA_CUDA(sl.h_scalars.ensure(B * 8));
     DLA_CUDA(sl.h_desc.ensure(cat_desc_layout(B, md).total));
     DLA_CUDA(sl.h_res.ensure(cat_res_layout(B, m, md).total));
-    DLA_CUDA(sl.h_alive.ensure(B * 4));
+    DLA_CUDA(sl.h_alive.ensure(B * CAT_ALIVE));
     if (o->sample_log_likelihoods_dla) DLA_CUDA(sl.h_sample_dla.ensure(B * S * md));
     if (o->sample_log_likelihoods_lls) DLA_CUDA(sl.h_sample_sub.ensure(B * S));
     if (o->base_sample_inds && md > 1) DLA_CUDA(sl.h_inds.ensure(B * S * (md - 1)));
@@ -351,7 +362,13 @@ static int cat_ensure_workspace(dla_catalogue* cat, size_t cap, bool host_source
   DLA_CUDA(cat->rows.ensure(B * S * md));
   DLA_CUDA(cat->inds_t.ensure(B * S * std::max<size_t>(md - 1, 1)));
   DLA_CUDA(cat->map_ind.ensure(B * md));
-  DLA_CUDA(cat->alive.ensure(B * 4));
+  DLA_CUDA(cat->alive.ensure(B * CAT_ALIVE));
+  DLA_CUDA(cat->sel.ensure(B * S));
+  DLA_CUDA(cat->pos_a.ensure(B * S));
+  DLA_CUDA(cat->pos_b.ensure(B * S));
+  DLA_CUDA(cat->rows0_c.ensure(B * S));
+  DLA_CUDA(cat->rows1_c.ensure(B * S));
+  DLA_CUDA(cat->raw_slots.ensure(B * S));
   DLA_CUDA(cat->res.ensure(cat_res_layout(B, m, md).total));
   DLA_CUDA(cat->desc.ensure(cat_desc_layout(B, md).total));
   return 0;
@@ -459,7 +476,7 @@ static int cat_enqueue_compute(dla_catalogue* cat, int bi, size_t cap, const dla
     cache_off[b] = cache_total;
     cache_total += (size_t)(2 * S + 1) * ld_b[b];
     prod_off[b] = prod_total;
-    if (md >= 3) prod_total += (size_t)S * ld_b[b];
+    if (md >= 3) prod_total += (size_t)S * ld_b[b] * (md >= 4 ? 2 : 1);  // ping-pong: level L reads what L - 1 wrote
     const size_t brows = round_up((size_t)std::max(sl.n_b[b], 1), LK_KC);
     basis_off[b] = basis_total;
     basis_total += brows * LK_PSTRIDE;
@@ -481,6 +498,11 @@ static int cat_enqueue_compute(dla_catalogue* cat, int bi, size_t cap, const dla
   EvidenceLevel* h_ev = reinterpret_cast<EvidenceLevel*>(hd + DL.ev);
   MapTask* h_map = reinterpret_cast<MapTask*>(hd + DL.map);
   GatherTask* h_gather = reinterpret_cast<GatherTask*>(hd + DL.gather);
+  CompactTask* h_compact = reinterpret_cast<CompactTask*>(hd + DL.compact);
+  const CompactTask* d_compact = reinterpret_cast<const CompactTask*>(cat->desc.p + DL.compact);
+  ScatterTask* h_scatter = reinterpret_cast<ScatterTask*>(hd + DL.scatter);
+  const ScatterTask* d_scatter = reinterpret_cast<const ScatterTask*>(cat->desc.p + DL.scatter);
+  sl.usable_b.assign(nb, 0);
   const GramBasisTask* d_basis = reinterpret_cast<const GramBasisTask*>(cat->desc.p + DL.basis);
   const AbsorptionGrid* d_grid = reinterpret_cast<const AbsorptionGrid*>(cat->desc.p + DL.grid);
   const LikelihoodSpectrum* d_lk = reinterpret_cast<const LikelihoodSpectrum*>(cat->desc.p + DL.lk);
@@ -493,10 +515,12 @@ static int cat_enqueue_compute(dla_catalogue* cat, int bi, size_t cap, const dla
     const PrepTask& pt = sl.h_prep.p[b];
     const int n = sl.n_b[b];
     const bool usable = n >= 1 && isfinite(h_scalars[(size_t)b * 8 + 3]) && isfinite(h_scalars[(size_t)b * 8 + 4]);
-    h_alive[(size_t)b * 4 + 0] = usable ? 1 : 0;
-    h_alive[(size_t)b * 4 + 1] = usable ? 0 : 1;  // status 1: nothing to model
-    h_alive[(size_t)b * 4 + 2] = usable ? 1 : 0;
-    h_alive[(size_t)b * 4 + 3] = 0;
+    h_alive[(size_t)b * CAT_ALIVE + 0] = usable ? 1 : 0;
+    h_alive[(size_t)b * CAT_ALIVE + 1] = usable ? 0 : 1;  // status 1: nothing to model
+    h_alive[(size_t)b * CAT_ALIVE + 2] = usable ? 1 : 0;
+    h_alive[(size_t)b * CAT_ALIVE + 3] = 0;
+    for (int level = 0; level < LK_MAX_ROWS; ++level) h_alive[(size_t)b * CAT_ALIVE + 4 + level] = 0;  // samples evaluated per level
+    sl.usable_b[b] = usable ? 1 : 0;
     double* cache_b = cat->cache.p + cache_off[b];
     h_basis[b].M = pt.M;
     h_basis[b].P = cat->basis.p + basis_off[b];
@@ -525,7 +549,7 @@ static int cat_enqueue_compute(dla_catalogue* cat, int bi, size_t cap, const dla
       d.P = cat->basis.p + basis_off[b];
       d.cache = cache_b;
       d.rows0 = nullptr;
-      d.alive = cat->alive.p + (size_t)b * 4;
+      d.alive = cat->alive.p + (size_t)b * CAT_ALIVE;
       d.n = n;
       d.ld = ld_b[b];
       d.row0 = 0;
@@ -538,21 +562,39 @@ static int cat_enqueue_compute(dla_catalogue* cat, int bi, size_t cap, const dla
         d.num_rows = 1;
         d.row_stride = 0;
       } else {
-        // Running product of the previous level (row s) x profile of the newly drawn absorber.
-        // In-place update at levels >= 2 (prod_out == base0): element (s, p) of the product buffer is read and
-        // written by exactly ONE thread of ONE CTA - the thread that owns pixel p of sample s in the tile that
-        // owns sample s - and that thread's store (scalar slot 0 of the panel's chain, after its cp.async of
-        // the same element has been waited for through the `full` barrier) is program-ordered after its own
-        // read of the staged copy.  No other CTA touches row s: factor 0 of sample s' is row s' of the
-        // buffer, never row s.  (Factor >= 1 rows come from the read-only profile cache.)
+        // Running product of the previous level x profile of the newly drawn absorber, over the samples that pass the
+        // separation test only (compact_level_kernel, launched just before): slot i evaluates sample sel[i]; its
+        // factor-0 row is rows0_c[i] (level 1: the sample's own profile in the cache; later: the slot it had in the
+        // previous level's launch, whose product rows are in slot order), its factor-1 row rows1_c[i] is the profile of
+        // the absorber drawn for this level.  Products ping-pong between two buffers (level L writes buffer L & 1 and
+        // reads buffer (L - 1) & 1), so no launch reads rows that the same launch writes.
         double* prod_b = cat->prod.p + prod_off[b];
-        d.base0 = level == 1 ? cache_b : prod_b;
-        d.rows = cat->rows.p + (size_t)b * S * md + (size_t)level * S;
-        d.prod_out = (level + 1 < md) ? prod_b : nullptr;
-        d.out = cat->raw_ll.p + (size_t)b * S;
-        d.num_samples = S;
+        const size_t prod_half = (size_t)S * ld_b[b];
+        double* prod_write = prod_b + ((md >= 4 && (level & 1) == 0) ? prod_half : 0);
+        const double* prod_read = prod_b + ((md >= 4 && ((level - 1) & 1) == 0) ? prod_half : 0);
+        d.base0 = level == 1 ? cache_b : prod_read;
+        d.rows0 = cat->rows0_c.p + (size_t)b * S;
+        d.rows = cat->rows1_c.p + (size_t)b * S;
+        d.prod_out = (level + 1 < md) ? prod_write : nullptr;
+        d.out = cat->raw_slots.p + (size_t)b * S;
+        d.num_samples = -(4 + level);  // the count is alive[4 + level], written by compact_level_kernel
         d.num_rows = 2;
         d.row_stride = S;
+        CompactTask ct;
+        ct.z_samples = cat->z_samples.p + (size_t)b * 2 * S;
+        ct.base_inds = cat->rows.p + (size_t)b * S * md + S;
+        ct.alive = cat->alive.p + (size_t)b * CAT_ALIVE;
+        ct.pos_prev = level == 1 ? nullptr : ((level & 1) ? cat->pos_b.p : cat->pos_a.p) + (size_t)b * S;
+        ct.pos = ((level & 1) ? cat->pos_a.p : cat->pos_b.p) + (size_t)b * S;
+        ct.sel = cat->sel.p + (size_t)b * S;
+        ct.rows0 = cat->rows0_c.p + (size_t)b * S;
+        ct.rows1 = cat->rows1_c.p + (size_t)b * S;
+        ct.raw_ll = cat->raw_ll.p + (size_t)b * S;
+        ct.num_sel = cat->alive.p + (size_t)b * CAT_ALIVE + 4 + level;
+        ct.S = S;
+        ct.level = level;
+        ct.min_z_separation = cat->params.min_z_separation;
+        h_compact[(size_t)level * nb + b] = ct;
       }
       h_lk[(size_t)level * nb + b] = d;
       EvidenceLevel e;
@@ -565,8 +607,8 @@ static int cat_enqueue_compute(dla_catalogue* cat, int bi, size_t cap, const dla
       e.uniforms = (level + 1 < md) ? cat->uniforms.p + (size_t)level * S : nullptr;
       e.log_evidence = cat->log_ev_dla.p + (size_t)b * md + level;
       e.cdf_scratch = cat->cdf.p + (size_t)b * S;
-      e.alive = cat->alive.p + (size_t)b * 4;
-      e.status = cat->alive.p + (size_t)b * 4 + 1;
+      e.alive = cat->alive.p + (size_t)b * CAT_ALIVE;
+      e.status = cat->alive.p + (size_t)b * CAT_ALIVE + 1;
       e.S = S;
       e.level = level;
       e.min_z_separation = cat->params.min_z_separation;
@@ -583,13 +625,19 @@ static int cat_enqueue_compute(dla_catalogue* cat, int bi, size_t cap, const dla
       e.uniforms = nullptr;
       e.log_evidence = cat->log_ev_sub.p + b;
       e.cdf_scratch = nullptr;
-      e.alive = cat->alive.p + (size_t)b * 4 + 2;  // not affected by the DLA model's early exit
+      e.alive = cat->alive.p + (size_t)b * CAT_ALIVE + 2;  // not affected by the DLA model's early exit
       e.status = nullptr;
       e.S = S;
       e.level = 0;
       e.min_z_separation = cat->params.min_z_separation;
       h_ev[(size_t)md * nb + b] = e;
     }
+    ScatterTask sc;
+    sc.raw_slots = cat->raw_slots.p + (size_t)b * S;
+    sc.sel = cat->sel.p + (size_t)b * S;
+    sc.num_sel = cat->alive.p + (size_t)b * CAT_ALIVE + 4;  // scatter_ll_kernel reads entry `level`
+    sc.raw_ll = cat->raw_ll.p + (size_t)b * S;
+    h_scatter[b] = sc;
     MapTask mt;
     mt.sample_ll = cat->sample_ll_dla.p + (size_t)b * S * md;
     mt.base_inds = cat->rows.p + (size_t)b * S * md + S;
@@ -611,7 +659,7 @@ static int cat_enqueue_compute(dla_catalogue* cat, int bi, size_t cap, const dla
     h_gather[b] = gt;
   }
   DLA_CUDA(cudaMemcpyAsync(cat->desc.p, hd, DL.total, cudaMemcpyHostToDevice, rt.stream));
-  DLA_CUDA(cudaMemcpyAsync(cat->alive.p, h_alive, sizeof(int) * nb * 4, cudaMemcpyHostToDevice, rt.stream));
+  DLA_CUDA(cudaMemcpyAsync(cat->alive.p, h_alive, sizeof(int) * nb * CAT_ALIVE, cudaMemcpyHostToDevice, rt.stream));
 
   // ---- launches ------------------------------------------------------------------------------
   auto fill = [&](double* p, size_t count, double value) -> int {
@@ -644,20 +692,26 @@ static int cat_enqueue_compute(dla_catalogue* cat, int bi, size_t cap, const dla
     return rc;
   DLA_CUDA(cudaEventRecord(sl.ev_v1, rt.stream));
   for (int level = 0; level < md; ++level) {
+    if (level > 0) {
+      compact_level_kernel<<<nb, 1024, 0, rt.stream>>>(d_compact + (size_t)level * nb);
+      DLA_LAUNCHED();
+    }
     DLA_CUDA(cudaEventRecord(sl.ev_lk[2 * level], rt.stream));
     const int ns = level == 0 ? 2 * S + 1 : S;
     dim3 grid((ns + LK_TS - 1) / LK_TS, nb);
     sample_likelihood_kernel<<<grid, LK_THREADS, LK_SMEM_BYTES, rt.stream>>>(d_lk + (size_t)level * nb);
     DLA_LAUNCHED();
     DLA_CUDA(cudaEventRecord(sl.ev_lk[2 * level + 1], rt.stream));
+    if (level > 0) {
+      scatter_ll_kernel<<<dim3((S + 255) / 256, nb), 256, 0, rt.stream>>>(d_scatter, level);
+      DLA_LAUNCHED();
+    }
     evidence_level_kernel<<<nb, 1024, 0, rt.stream>>>(d_ev + (size_t)level * nb);
     DLA_LAUNCHED();
     if (level == 0) {
       evidence_level_kernel<<<nb, 1024, 0, rt.stream>>>(d_ev + (size_t)md * nb);
       DLA_LAUNCHED();
     }
-    for (int b = 0; b < nb; ++b)
-      if (h_alive[(size_t)b * 4]) cat->gram_flops += (double)ns * (472.0 * sl.n_b[b] + 3.1e3);
   }
   {
     dim3 grid(md, nb);
@@ -677,7 +731,7 @@ static int cat_enqueue_compute(dla_catalogue* cat, int bi, size_t cap, const dla
   }
   // ---- results -> the slot's page-locked staging (the host picks them up one batch later) ----------------
   DLA_CUDA(cudaMemcpyAsync(sl.h_res.p, res, sizeof(double) * RL.total, cudaMemcpyDeviceToHost, rt.stream));
-  DLA_CUDA(cudaMemcpyAsync(sl.h_alive.p, cat->alive.p, sizeof(int) * nb * 4, cudaMemcpyDeviceToHost, rt.stream));
+  DLA_CUDA(cudaMemcpyAsync(sl.h_alive.p, cat->alive.p, sizeof(int) * nb * CAT_ALIVE, cudaMemcpyDeviceToHost, rt.stream));
   if (o->sample_log_likelihoods_dla)
     DLA_CUDA(cudaMemcpyAsync(sl.h_sample_dla.p, cat->sample_ll_dla.p, sizeof(double) * nb * S * md, cudaMemcpyDeviceToHost, rt.stream));
   if (o->sample_log_likelihoods_lls)
@@ -717,7 +771,21 @@ static int cat_consume(dla_catalogue* cat, int bi, dla_catalogue_outputs* o) {
     if (o->min_z_dlas) o->min_z_dlas[q0 + b] = sl.zmin_b[b];
     if (o->max_z_dlas) o->max_z_dlas[q0 + b] = sl.zmax_b[b];
     if (o->num_pixels) o->num_pixels[q0 + b] = sl.n_b[b];
-    if (o->status) o->status[q0 + b] = sl.h_alive.p[b * 4 + 1];
+    if (o->status) o->status[q0 + b] = sl.h_alive.p[b * CAT_ALIVE + 1];
+  }
+  // algorithmic work of the likelihood launches: the evaluations that were run (masked samples are not evaluated)
+  for (size_t b = 0; b < nb; ++b) {
+    if (!sl.usable_b[b]) continue;
+    const double per_eval = 472.0 * sl.n_b[b] + 3.1e3;
+    long long evals = 2 * (long long)S + 1;
+    for (size_t level = 1; level < md; ++level) {
+      const int kept = sl.h_alive.p[b * CAT_ALIVE + 4 + level];
+      evals += kept;
+      // a spectrum that left the level loop (NaN evidence) has kept == 0 and nothing masked
+      if (kept > 0 || sl.h_alive.p[b * CAT_ALIVE] != 0) cat->lk_masked += (long long)S - kept;
+    }
+    cat->lk_evaluated += evals;
+    cat->gram_flops += (double)evals * per_eval;
   }
   float ms = 0.f;
   DLA_CUDA(cudaEventElapsedTime(&ms, sl.ev_v0, sl.ev_v1));
@@ -735,6 +803,7 @@ static int cat_run(dla_catalogue* cat, const CatSource& src, const double* d_log
   int rc = cat_ensure_workspace(cat, cap, !src.on_device, o);
   if (rc) return rc;
   cat->total_ms = cat->gram_ms = cat->voigt_ms = cat->gram_flops = 0;
+  cat->lk_evaluated = cat->lk_masked = 0;
   const long long launches_before = rt.launches;
   const PrepParams P = to_prep_params(&cat->params, 1);
   const int nbatches = (src.Q + cat->B - 1) / cat->B;
@@ -816,6 +885,13 @@ extern "C" int dla_catalogue_process(dla_catalogue* cat, int num_spectra, const 
   DLA_CUDA(cat->log_priors_call.ensure((size_t)num_spectra * m));
   DLA_CUDA(cat->log_priors_call.upload(log_priors_in, (size_t)num_spectra * m, rt.stream));
   return cat_run(cat, src, cat->log_priors_call.p, outputs);
+}
+
+extern "C" int dla_catalogue_last_counts(const dla_catalogue* cat, long long* evaluated, long long* masked) {
+  DLA_REQUIRE(cat, "null catalogue");
+  if (evaluated) *evaluated = cat->lk_evaluated;
+  if (masked) *masked = cat->lk_masked;
+  return 0;
 }
 
 extern "C" int dla_catalogue_last_timing(const dla_catalogue* cat, double* total_ms, double* gram_ms, double* voigt_ms,

@@ -163,8 +163,11 @@ struct dla_spectrum {
   DevBuf<int32_t> uidx, qmap;
   // work buffers (grown on demand)
   DevBuf<double> cache, prod, z_dev, nhi_dev, uniforms, raw_ll, sample_ll, log_ev, cdf;
-  DevBuf<int32_t> rows;
-  DevBuf<int> alive;
+  DevBuf<int32_t> rows, sel, pos_a, pos_b, rows0_c, rows1_c;
+  DevBuf<double> raw_slots;
+  DevBuf<int> alive;  // [0] alive, [1] status, [4 + level] samples evaluated at that level
+  DevBuf<CompactTask> compact_desc;
+  DevBuf<ScatterTask> scatter_desc;
   DevBuf<LikelihoodSpectrum> lk_desc;
   DevBuf<EvidenceLevel> ev_desc;
   DevBuf<AbsorptionGrid> grid_desc;
@@ -866,31 +869,67 @@ extern "C" int dla_log_model_evidences(dla_spectrum* sp, const double* z_samples
   int rc = ensure_cache(sp, S);
   if (rc) return rc;
   if ((rc = ensure_basis(sp))) return rc;
-  if (max_dlas >= 3) DLA_CUDA(sp->prod.ensure((size_t)S * sp->ld));
+  const size_t prod_half = (size_t)S * sp->ld;
+  if (max_dlas >= 3) DLA_CUDA(sp->prod.ensure(prod_half * (max_dlas >= 4 ? 2 : 1)));  // ping-pong, see catalogue.inc.cuh
   DLA_CUDA(sp->raw_ll.ensure(S));
   DLA_CUDA(sp->sample_ll.ensure((size_t)S * max_dlas));
   DLA_CUDA(sp->log_ev.ensure(max_dlas));
   DLA_CUDA(sp->cdf.ensure(S));
   DLA_CUDA(sp->rows.ensure((size_t)S * max_dlas));
-  DLA_CUDA(sp->alive.ensure(2));
+  DLA_CUDA(sp->alive.ensure(4 + LK_MAX_ROWS));
   DLA_CUDA(sp->lk_desc.ensure(16));
   DLA_CUDA(sp->ev_desc.ensure(16));
+  DLA_CUDA(sp->sel.ensure(S));
+  DLA_CUDA(sp->pos_a.ensure(S));
+  DLA_CUDA(sp->pos_b.ensure(S));
+  DLA_CUDA(sp->rows0_c.ensure(S));
+  DLA_CUDA(sp->rows1_c.ensure(S));
+  DLA_CUDA(sp->raw_slots.ensure(S));
+  DLA_CUDA(sp->compact_desc.ensure(16));
+  DLA_CUDA(sp->scatter_desc.ensure(1));
 
   // descriptors of all levels (they do not depend on results)
   std::vector<LikelihoodSpectrum> lk(max_dlas);
   std::vector<EvidenceLevel> ev(max_dlas);
+  std::vector<CompactTask> compact(max_dlas);
   for (int level = 0; level < max_dlas; ++level) {
     LikelihoodSpectrum d = base_desc(sp);
     d.out = sp->raw_ll.p;
     d.num_samples = S;
-    // level L >= 1 multiplies the running product of level L-1 (row s of `prod`, or the sample's own
-    // profile at L == 1) by the profile of the newly drawn absorber base_sample_inds[L-1][s]
-    d.num_rows = level == 0 ? 1 : 2;
-    d.base0 = level <= 1 ? sp->cache.p : sp->prod.p;
-    d.rows = level == 0 ? nullptr : sp->rows.p + (size_t)level * S;
-    d.row_stride = S;
-    d.prod_out = (level >= 1 && level + 1 < max_dlas) ? sp->prod.p : nullptr;
+    // level L >= 1 multiplies the running product of level L-1 by the profile of the newly drawn absorber
+    // base_sample_inds[L-1][s], for the samples that pass the separation test only: compacted launch in slot order,
+    // products ping-pong between two buffers (same scheme as the catalogue engine, catalogue.inc.cuh)
     d.alive = sp->alive.p;
+    if (level == 0) {
+      d.num_rows = 1;
+      d.base0 = sp->cache.p;
+    } else {
+      double* prod_write = sp->prod.p + ((max_dlas >= 4 && (level & 1) == 0) ? prod_half : 0);
+      const double* prod_read = sp->prod.p + ((max_dlas >= 4 && ((level - 1) & 1) == 0) ? prod_half : 0);
+      d.num_rows = 2;
+      d.base0 = level == 1 ? sp->cache.p : prod_read;
+      d.rows0 = sp->rows0_c.p;
+      d.rows = sp->rows1_c.p;
+      d.row_stride = S;
+      d.prod_out = (level + 1 < max_dlas) ? prod_write : nullptr;
+      d.out = sp->raw_slots.p;
+      d.num_samples = -(4 + level);  // the count is alive[4 + level], written by compact_level_kernel
+    }
+    CompactTask ct;
+    ct.z_samples = sp->z_dev.p;
+    ct.base_inds = sp->rows.p + S;
+    ct.alive = sp->alive.p;
+    ct.pos_prev = level <= 1 ? nullptr : ((level & 1) ? sp->pos_b.p : sp->pos_a.p);
+    ct.pos = (level & 1) ? sp->pos_a.p : sp->pos_b.p;
+    ct.sel = sp->sel.p;
+    ct.rows0 = sp->rows0_c.p;
+    ct.rows1 = sp->rows1_c.p;
+    ct.raw_ll = sp->raw_ll.p;
+    ct.num_sel = sp->alive.p + 4 + level;
+    ct.S = S;
+    ct.level = level;
+    ct.min_z_separation = min_z_separation;
+    compact[level] = ct;
     lk[level] = d;
     EvidenceLevel e;
     e.raw_ll = sp->raw_ll.p;
@@ -911,7 +950,14 @@ extern "C" int dla_log_model_evidences(dla_spectrum* sp, const double* z_samples
   }
   DLA_CUDA(cudaMemcpyAsync(sp->lk_desc.p, lk.data(), sizeof(LikelihoodSpectrum) * max_dlas, cudaMemcpyHostToDevice, rt.stream));
   DLA_CUDA(cudaMemcpyAsync(sp->ev_desc.p, ev.data(), sizeof(EvidenceLevel) * max_dlas, cudaMemcpyHostToDevice, rt.stream));
-  const int alive_init[2] = {1, 0};
+  DLA_CUDA(cudaMemcpyAsync(sp->compact_desc.p, compact.data(), sizeof(CompactTask) * max_dlas, cudaMemcpyHostToDevice, rt.stream));
+  ScatterTask sc;
+  sc.raw_slots = sp->raw_slots.p;
+  sc.sel = sp->sel.p;
+  sc.num_sel = sp->alive.p + 4;
+  sc.raw_ll = sp->raw_ll.p;
+  DLA_CUDA(cudaMemcpyAsync(sp->scatter_desc.p, &sc, sizeof(sc), cudaMemcpyHostToDevice, rt.stream));
+  int alive_init[4 + LK_MAX_ROWS] = {1, 0};
   DLA_CUDA(cudaMemcpyAsync(sp->alive.p, alive_init, sizeof(alive_init), cudaMemcpyHostToDevice, rt.stream));
 
   KernelTimer timer;
@@ -926,8 +972,16 @@ extern "C" int dla_log_model_evidences(dla_spectrum* sp, const double* z_samples
   rc = launch_voigt(sp, sp->z_dev.p, sp->nhi_dev.p, S, num_lines, sp->cache.p, sp->ld);
   if (rc) return rc;
   for (int level = 0; level < max_dlas; ++level) {
+    if (level > 0) {
+      compact_level_kernel<<<1, 1024, 0, rt.stream>>>(sp->compact_desc.p + level);
+      DLA_LAUNCHED();
+    }
     rc = launch_likelihood(sp->lk_desc.p + level, S, 1);
     if (rc) return rc;
+    if (level > 0) {
+      scatter_ll_kernel<<<dim3((S + 255) / 256, 1), 256, 0, rt.stream>>>(sp->scatter_desc.p, level);
+      DLA_LAUNCHED();
+    }
     evidence_level_kernel<<<1, 1024, 0, rt.stream>>>(sp->ev_desc.p + level);
     DLA_LAUNCHED();
   }

@@ -102,7 +102,10 @@ struct LikelihoodSpectrum {
   double* out;           // num_samples raw log-likelihoods
   int n;                 // modelled pixels
   int ld;                // profile row stride
-  int num_samples;       // samples in this launch
+  int num_samples;       // samples in this launch; a NEGATIVE value -i means "read the count from alive[i]": the launch
+                         // was compacted on the device (compact_level_kernel; rows0 / rows / prod_out / out are then in
+                         // slot order).  Encoded in the existing field because growing this struct by one pointer
+                         // changed ptxas's register allocation of the main loop (8-byte spill per panel).
   int num_rows;          // factors per sample (1..LK_MAX_ROWS)
   int row_stride;        // stride between factor arrays in `rows`
   int row0;              // first profile row when the row arrays are null
@@ -262,10 +265,11 @@ static_assert(LK_PANEL_BYTES % 128 == 0, "TMA alignment");
 __global__ void __launch_bounds__(LK_THREADS, LK_CTAS_PER_SM)
 sample_likelihood_kernel(const LikelihoodSpectrum* __restrict__ specs) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
-  const LikelihoodSpectrum sp = specs[blockIdx.y];
+  LikelihoodSpectrum sp = specs[blockIdx.y];
   const int tile_s0 = blockIdx.x * LK_TS;
-  if (tile_s0 >= sp.num_samples) return;
   if (sp.alive && *sp.alive == 0) return;
+  if (sp.num_samples < 0) sp.num_samples = sp.alive[-sp.num_samples];
+  if (tile_s0 >= sp.num_samples) return;
 
   double* s_main = reinterpret_cast<double*>(smem_raw);
   double* s_WG = s_main + LK_PSTAGES * LK_PANEL_DOUBLES;  // 2 buffers x { W [32][20], G [32][20] }
@@ -682,9 +686,9 @@ sample_likelihood_kernel(const LikelihoodSpectrum* __restrict__ specs) {
 #pragma unroll
       for (int k = 0; k < LK_K; k += 2) { zz0 = fma(r2[k], r2[k], zz0); zz1 = fma(r2[k + 1], r2[k + 1], zz1); }
       const double quad = s_sums[s * 3] - (zz0 + zz1);
-      // sum log d + 2 sum log L_ii; a pivot product that is not a positive number (zero, negative, NaN) poisons the sample
-      const double pp = piv_prod > 0.0 ? piv_prod : __longlong_as_double(0x7ff8000000000000ll);
-      const double log_det = fma(s_sums[s * 3 + 2] + (double)piv_exp, LK_LN2, log(s_sums[s * 3 + 1] * pp));
+      // sum log d + 2 sum log L_ii.  A zero, negative or NaN pivot has already poisoned the factor through fast_rsqrt
+      // (inf / NaN), so quad is NaN and the sample with it: no +inf can come out of log(0) here
+      const double log_det = fma(s_sums[s * 3 + 2] + (double)piv_exp, LK_LN2, log(s_sums[s * 3 + 1] * piv_prod));
       sp.out[tile_s0 + s] = -0.5 * (quad + log_det + (double)n * LK_LOG_2PI);
     }
   }

@@ -212,8 +212,10 @@ class CatalogueProcessor:
                 ctypes.byref(flops),
             )
         )
+        ev, mk = ctypes.c_longlong(), ctypes.c_longlong()
+        _lib.check(_lib.load_library().dla_catalogue_last_counts(self._cat.ptr, ctypes.byref(ev), ctypes.byref(mk)))
         return dict(total_ms=total.value, likelihood_ms=gram.value, voigt_ms=voigt.value, launches=launches.value,
-                    likelihood_flops=flops.value)
+                    likelihood_flops=flops.value, evaluations=ev.value, evaluations_masked=mk.value)
 
     def _finish(self, out: Dict[str, np.ndarray]) -> Dict[str, np.ndarray]:
         """Split the (Q, 2+max) arrays into the reference's dataset names (run_bayes_select.py:197-209)."""

@@ -203,6 +203,10 @@ int dla_catalogue_run_staged(dla_catalogue* cat, dla_catalogue_outputs* outputs)
 int dla_catalogue_last_timing(const dla_catalogue* cat, double* total_ms, double* gram_ms,
                               double* voigt_ms, long long* launches, double* gram_flops);
 
+/* likelihood evaluations of the last process/run call: how many were run, and how many samples of levels >= 1 were
+ * left out because the separation test (dla_gp.py:164-177) turns their result into NaN whatever its value */
+int dla_catalogue_last_counts(const dla_catalogue* cat, long long* evaluated, long long* masked);
+
 /* ---- a14: quasar-redshift estimation, ZGP (zqso_gp.py) ---------------------------------- */
 typedef struct dla_zqso_model dla_zqso_model; /* learned zQSO model resident on the device */
 /* ZGP.__init__ (zqso_gp.py:36-64): rest grid (n_rest), mu (n_rest), M (n_rest, k = 20) row-major, and the
