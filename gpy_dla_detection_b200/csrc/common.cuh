@@ -56,6 +56,46 @@ int ensure_ready();
     DLA_CUDA(cudaGetLastError());      \
   } while (0)
 
+// Free list of large device allocations.  The class API creates one dla_spectrum per set_data call (three per
+// spectrum: null, subDLA, DLA model) and each grows a profile cache, product buffers and a Gram basis of tens to
+// hundreds of MB; cudaMalloc + cudaFree of those (cudaFree synchronises the device) dominated the per-spectrum
+// latency.  Buffers of at least POOL_MIN_BYTES go back to this list when their owner dies and are handed to the next
+// request they fit (first fit, at most 2x oversize); the list is bounded and flushed when dla_init changes device.
+struct BufferPool {
+  static constexpr size_t POOL_MIN_BYTES = (size_t)1 << 20;
+  static constexpr size_t POOL_MAX_ENTRIES = 24;
+  static constexpr size_t POOL_MAX_ENTRY_BYTES = (size_t)1 << 30;   // catalogue-sized buffers are simply freed
+  static constexpr size_t POOL_MAX_TOTAL_BYTES = (size_t)4 << 30;
+  struct Entry { void* p; size_t bytes; };
+  std::vector<Entry> free_list;
+  size_t total_bytes = 0;
+  void* take(size_t bytes, size_t* got) {
+    for (size_t i = 0; i < free_list.size(); ++i)
+      if (free_list[i].bytes >= bytes && free_list[i].bytes <= 2 * bytes) {
+        void* p = free_list[i].p;
+        *got = free_list[i].bytes;
+        total_bytes -= free_list[i].bytes;
+        free_list.erase(free_list.begin() + i);
+        return p;
+      }
+    return nullptr;
+  }
+  bool give(void* p, size_t bytes) {
+    if (bytes < POOL_MIN_BYTES || bytes > POOL_MAX_ENTRY_BYTES || free_list.size() >= POOL_MAX_ENTRIES ||
+        total_bytes + bytes > POOL_MAX_TOTAL_BYTES)
+      return false;
+    free_list.push_back({p, bytes});
+    total_bytes += bytes;
+    return true;
+  }
+  void flush() {
+    for (Entry& e : free_list) cudaFree(e.p);
+    free_list.clear();
+    total_bytes = 0;
+  }
+};
+BufferPool& buffer_pool();
+
 template <typename T>
 struct DevBuf {
   T* p = nullptr;
@@ -65,13 +105,21 @@ struct DevBuf {
   DevBuf& operator=(const DevBuf&) = delete;
   ~DevBuf() { release(); }
   void release() {
-    if (p) cudaFree(p);
+    if (p && !buffer_pool().give(p, n * sizeof(T))) cudaFree(p);
     p = nullptr;
     n = 0;
   }
   cudaError_t alloc(size_t count) {
     release();
     if (count == 0) count = 1;
+    if (count * sizeof(T) >= BufferPool::POOL_MIN_BYTES) {
+      size_t got = 0;
+      if (void* q = buffer_pool().take(count * sizeof(T), &got)) {
+        p = static_cast<T*>(q);
+        n = got / sizeof(T);
+        return cudaSuccess;
+      }
+    }
     cudaError_t e = cudaMalloc(&p, count * sizeof(T));
     if (e == cudaSuccess) n = count;
     return e;

@@ -30,6 +30,10 @@ Runtime& runtime() {
   static Runtime rt;
   return rt;
 }
+BufferPool& buffer_pool() {
+  static BufferPool pool;
+  return pool;
+}
 void set_error(const std::string& msg) { t_error = msg; }
 int fail(const std::string& msg) {
   t_error = msg;
@@ -50,6 +54,7 @@ static int init_device(int device) {
   DLA_CUDA(cudaGetDeviceProperties(&prop, device));
   if (prop.major < 10) return fail(std::string("device '") + prop.name + "' is not sm_100-class; this library is built for sm_100a only");
   if (rt.stream) {
+    buffer_pool().flush();  // pooled allocations belong to the device being left
     cudaStreamDestroy(rt.stream);
     if (rt.copy_stream) cudaStreamDestroy(rt.copy_stream);
     cudaEventDestroy(rt.ev_begin);
