@@ -195,3 +195,32 @@ def test_patch_reference_installs_and_restores():
     for (c, n), old in before.items():
         assert c.__dict__.get(n) is old, (c, n)
     assert rv.voigt_absorption is ref_voigt and rd.voigt_absorption is ref_voigt
+
+
+def test_bench_reference_arm_line_and_config_identity():
+    """
+    `bench.py --impl reference` (the CPU arm the driver divides by): one JSON line with the contract's keys, the
+    live reference as implementation when it is staged, and a `config` object identical to the GPU arm's.
+    """
+    import json
+
+    env = dict(os.environ, OMP_NUM_THREADS="1")
+    res = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0",
+                          "--ref-fraction", "200"], capture_output=True, text=True, timeout=600, env=env, cwd=ROOT)
+    assert res.returncode == 0, res.stderr[-3000:]
+    line = json.loads(res.stdout.strip().splitlines()[-1])
+    for key in ("impl", "metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
+                "dtype", "data", "config", "cpu_baseline", "e2e"):
+        assert key in line, key
+    assert line["impl"] == "reference" and line["unit"] == "spectra/s" and line["value"] > 0
+    assert line["e2e"] == {"value": line["value"], "unit": "spectra/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    cb = line["cpu_baseline"]
+    assert cb["kind"] in ("reference", "port") and 1 <= cb["cores"] <= 16 and cb["sample_fraction"] == 1.0 / 200
+    from oracle import ref_loader
+
+    assert cb["kind"] == ("reference" if ref_loader.reference_available() else "port")
+    sys.path.insert(0, ROOT)
+    import bench
+
+    assert line["config"] == bench.workload_config(1, bench.CONFIGS[1]["spectra"])  # what the GPU arm prints
+    assert line["metric"] == bench.CONFIGS[1]["metric"]
