@@ -215,23 +215,32 @@ class CpuArm:
                 if steps_planned * per_spectrum / f <= budget_s:
                     fraction = f
                     break
-        self.fraction = int(fraction)
-        self.S = max(c["S"] // self.fraction, 8)
         n = self.workers
         if c["kind"] == "dla":
-            params, model, prior, dla, sub, z_qsos, spectra = synthetic.make_workload(n, 0, c["S"], c["num_lines"])
+            self._inputs = synthetic.make_workload(n, 0, c["S"], c["num_lines"])
+        else:
+            self._inputs = synthetic.make_zqso_workload(n, 0)
+        self.set_fraction(fraction)
+        for var in ("OMP_NUM_THREADS", "OPENBLAS_NUM_THREADS", "MKL_NUM_THREADS"):
+            os.environ[var] = "1"  # inherited by the spawned workers before they import NumPy
+        self.pool = mp.get_context("spawn").Pool(self.workers, initializer=_cpu_init, initargs=(1,))
+        self.pool.map(abs, range(self.workers))  # workers up, imports done (untimed)
+
+    def set_fraction(self, fraction):
+        """(Re)build the step's jobs for 1/fraction of the samples of every spectrum."""
+        c, n = self.cfg, self.workers
+        self.fraction = int(fraction)
+        self.S = max(c["S"] // self.fraction, 8)
+        if c["kind"] == "dla":
+            params, model, prior, dla, sub, z_qsos, spectra = self._inputs
             dla_f = {k: (v[: self.S] if np.ndim(v) else v) for k, v in dla.items()}
             sub_f = {k: (v[: self.S] if np.ndim(v) else v) for k, v in sub.items()}
             self.jobs = [dict(kind="dla", impl=self.impl, model=model, dla=dla_f, sub=sub_f, prior=prior,
                               spectrum=spectra[i], z_qso=float(z_qsos[i]), S=self.S, max_dlas=c["max_dlas"],
                               num_lines=c["num_lines"]) for i in range(n)]
         else:
-            model, z_true, spectra = synthetic.make_zqso_workload(n, 0)
+            model, z_true, spectra = self._inputs
             self.jobs = [dict(kind="zqso", impl=self.impl, model=model, spectrum=spectra[i], S=self.S) for i in range(n)]
-        for var in ("OMP_NUM_THREADS", "OPENBLAS_NUM_THREADS", "MKL_NUM_THREADS"):
-            os.environ[var] = "1"  # inherited by the spawned workers before they import NumPy
-        self.pool = mp.get_context("spawn").Pool(self.workers, initializer=_cpu_init, initargs=(1,))
-        self.pool.map(abs, range(self.workers))  # workers up, imports done (untimed)
 
     def step(self):
         """One pass over the step's spectra; returns seconds."""
@@ -268,7 +277,21 @@ def run_reference_arm(args):
     c = CONFIGS[args.config]
     arm = CpuArm(args.config, fraction=args.ref_fraction, steps_planned=args.steps + args.warmup, budget_s=args.ref_budget)
     times = []
-    for it in range(args.warmup + args.steps):
+    done = 0
+    if args.ref_fraction is None and args.warmup >= 1:
+        # The first warm-up step doubles as a calibration of THIS host: the static per-spectrum estimates come from the
+        # build container, whose cores are half as fast as the B200 box's.  Use the largest share of the samples
+        # (smallest divisor) with which the remaining steps still fit the budget.
+        t_probe = arm.step()
+        done = 1
+        t_full = t_probe * arm.fraction
+        remaining = args.steps + args.warmup - 1
+        for f in FRACTIONS:
+            if remaining * t_full / f <= args.ref_budget - t_probe:
+                if f != arm.fraction:
+                    arm.set_fraction(f)
+                break
+    for it in range(done, args.warmup + args.steps):
         dt = arm.step()
         if it >= args.warmup:
             times.append(dt)
