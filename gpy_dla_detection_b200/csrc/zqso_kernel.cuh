@@ -561,6 +561,9 @@ __device__ __forceinline__ double zq_rsqrt(double x) {
 #ifndef ZQ2_SCALAR_FIRST
 #define ZQ2_SCALAR_FIRST 0
 #endif
+#ifndef ZQ2_LOCKSTEP
+#define ZQ2_LOCKSTEP 0   // experiment: CTA barrier every ZQ2_LOCKSTEP chunks so that the warps (adjacent redshifts) hit the same table rows
+#endif
 __global__ void __launch_bounds__(ZQ2_WARPS * 32, ZQ2_MIN_CTAS)
 zqso_likelihood_kernel_v2(const ZqsoSpectrum* __restrict__ spectra, const double* __restrict__ z_samples, int S,
                           const double* __restrict__ med_all, ZqsoModelDev model, ZqsoParamsDev prm,
@@ -657,6 +660,14 @@ zqso_likelihood_kernel_v2(const ZqsoSpectrum* __restrict__ spectra, const double
   // step: long_scoreboard 33 %; third: operands shuffled at the end of the step that uses them next: short_scoreboard
   // on the first DMMAs).
   const int nchunks = whi > wlo ? (whi - wlo + 31) >> 5 : 0;
+#if ZQ2_LOCKSTEP
+  __shared__ int s_min_chunks;
+  if (threadIdx.x == 0) s_min_chunks = 0x7fffffff;
+  __syncthreads();
+  if (lane == 0) atomicMin(&s_min_chunks, nchunks);
+  __syncthreads();
+  const int lock_chunks = s_min_chunks;  // every warp of the CTA runs at least this many chunks
+#endif
   if (nchunks > 0) {
     double* rec0 = buf;
     double* rec1 = buf + 32 * ZQ2_REC;
@@ -689,6 +700,9 @@ zqso_likelihood_kernel_v2(const ZqsoSpectrum* __restrict__ spectra, const double
       double* cur = (c & 1) ? rec1 : rec0;
       double* nxt = (c & 1) ? rec0 : rec1;
       if ((c & 7) == 7) vprod.renorm();
+#if ZQ2_LOCKSTEP
+      if (c < lock_chunks && (c % ZQ2_LOCKSTEP) == 0) __syncthreads();
+#endif
 #pragma unroll
       for (int kb = 0; kb < 8; ++kb) {
         if (kb == 0) __syncwarp();                      // every lane has read its last record of chunk c - 1 from `nxt`

@@ -7,8 +7,7 @@ sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), ".."
 import numpy as np
 import __graft_entry__ as g
 g.build()
-import bench
-from gpy_dla_detection_b200 import _lib
+from gpy_dla_detection_b200 import _lib, synthetic
 from gpy_dla_detection_b200.run_bayes_select import CatalogueProcessor
 from gpy_dla_detection_b200.dla_samples import DLASamplesArrays
 from gpy_dla_detection_b200.subdla_samples import SubDLASamplesArrays
@@ -16,11 +15,11 @@ from gpy_dla_detection_b200.subdla_samples import SubDLASamplesArrays
 repeats = int(sys.argv[1]) if len(sys.argv) > 1 else 10
 Q = int(sys.argv[2]) if len(sys.argv) > 2 else 1000
 _lib.init(0)
-params, model, prior, dla, sub, z_qsos, spectra = bench.make_workload(Q)
+params, model, prior, dla, sub, z_qsos, spectra = synthetic.make_workload(Q)
 dla_s = DLASamplesArrays(params, prior, dla["offset_samples"], dla["log_nhi_samples"], dla["nhi_samples"])
 sub_s = SubDLASamplesArrays(params, prior, sub["offset_samples"], sub["log_nhi_samples"], sub["nhi_samples"],
                             sub["Z_lls"], sub["Z_dla"])
-proc = CatalogueProcessor(params, prior, model, dla_s, sub_s, bench.MAX_DLAS, True, batch_spectra=128)
+proc = CatalogueProcessor(params, prior, model, dla_s, sub_s, 4, True, batch_spectra=128)
 offsets, wl, fl, nv, pm = proc.pack(spectra)
 first = None
 t0 = time.perf_counter()
