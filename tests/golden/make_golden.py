@@ -347,7 +347,45 @@ def golden_bench_sweep(workers=None):
     print("p_dla:", np.round(out["p_dla"], 4))
 
 
+ZQSO_SWEEP_INDICES = (0, 1, 2, 3, 5, 8, 13, 21)  # spectra of bench.py's configs[4] workload (make_zqso_workload(Q, 0))
+
+
+def _zqso_sweep_one(i):
+    model, z_true, spectra = synthetic.make_zqso_workload(max(ZQSO_SWEEP_INDICES) + 1, 0)
+    t0 = time.time()
+    ll, z_map = ref_loader.run_reference_zqso(model, spectra[i], 10000)
+    return dict(index=i, z_true=float(z_true[i]), z_map=float(z_map), ll_strided=ll[::SWEEP_STRIDE], ll_sha_nan=_sha(np.isnan(ll)),
+                argmax=int(np.nanargmax(ll)), ll_max=float(np.nanmax(ll)), reference_seconds=time.time() - t0)
+
+
+def golden_zqso_sweep(workers=None):
+    """
+    ZGP.inference_z_qso of the live reference (10 000 z samples) on 8 spectra OF THE BENCH WORKLOAD of configs[4]:
+    every 8th sample log-likelihood, the NaN pattern's hash, the argmax and z_MAP.  About 30-60 s per spectrum per core.
+    """
+    import contextlib
+    import io
+    import multiprocessing as mp
+
+    workers = workers or min(os.cpu_count() or 1, len(ZQSO_SWEEP_INDICES))
+    with contextlib.redirect_stdout(io.StringIO()):
+        with mp.get_context("fork").Pool(workers) as pool:
+            rows = pool.map(_zqso_sweep_one, ZQSO_SWEEP_INDICES, chunksize=1)
+    out = {"indices": np.array(ZQSO_SWEEP_INDICES), "stride": SWEEP_STRIDE}
+    for key in rows[0]:
+        if key == "index":
+            continue
+        vals = [r[key] for r in rows]
+        out[key] = np.array(vals) if not isinstance(vals[0], str) else np.array(vals, dtype="U64")
+    np.savez_compressed(os.path.join(HERE, "zqso_bench_sweep_S10000.npz"), **out)
+    print("zqso_bench_sweep_S10000.npz written; z_true", np.round(out["z_true"], 3), "z_map", np.round(out["z_map"], 3),
+          "seconds", np.round(out["reference_seconds"], 1))
+
+
 if __name__ == "__main__":
+    if "--only-zqso-sweep" in sys.argv:
+        golden_zqso_sweep()
+        sys.exit(0)
     if "--only-sweep" in sys.argv:
         golden_bench_sweep()
         sys.exit(0)

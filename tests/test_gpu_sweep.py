@@ -72,3 +72,51 @@ def test_config3_whole_columns_short_spectrum(gpu):
     assert np.argmax(out["model_posteriors"][0]) == np.argmax(ref["model_posteriors"])
     assert np.array_equal(out["MAP_z_dlas"][0], ref["MAP_z_dlas"], equal_nan=True)
     assert np.array_equal(out["MAP_log_nhis"][0], ref["MAP_log_nhis"], equal_nan=True)
+
+
+def _zqso_oracle_one(job):
+    from oracle import zqso_oracle as ZO
+
+    model, spec, zs = job
+    out = ZO.inference_z_qso(model, *spec, zs)
+    return out["sample_log_likelihoods"], float(out["z_map"])
+
+
+def test_zqso_bench_workload_against_live_reference_goldens_and_oracle(gpu):
+    """
+    configs[4] at the published size (10 000 z_QSO samples per spectrum) on spectra of bench.py's own workload: the
+    round-2 ZGP kernels vs (a) the live reference's output for 8 of them (tests/golden/zqso_bench_sweep_S10000.npz) and
+    (b) the oracle on every 10th redshift sample of 16 of them, on the box's host cores.
+    """
+    import multiprocessing as mp
+
+    from gpy_dla_detection_b200 import synthetic
+    from gpy_dla_detection_b200.zqso_gp import ZGP
+    from gpy_dla_detection_b200.zqso_samples import ZSamples
+    from gpy_dla_detection_b200.zqso_set_parameters import ZParameters
+
+    Q = 22
+    model, z_true, spectra = synthetic.make_zqso_workload(Q, 0)
+    p = ZParameters(num_zqso_samples=10000)
+    gp = ZGP(p, ZSamples(p), model["rest_wavelengths"], model["mu"], model["M"], model["bluewards_mu"], model["redwards_mu"],
+             model["bluewards_sigma"], model["redwards_sigma"])
+    zs = ZSamples(p).sample_z_qsos()
+    out = gp.inference_z_qsos(spectra, zs)
+    ll = out["sample_log_likelihoods"]
+    # (a) live reference
+    g = H.golden("zqso_bench_sweep_S10000.npz")
+    stride = int(g["stride"])
+    for j, q in enumerate(g["indices"]):
+        q = int(q)
+        assert float(g["z_true"][j]) == float(z_true[q])
+        assert H.ll_err(ll[q][::stride], g["ll_strided"][j]) < 1e-9, q
+        assert int(out["map_index"][q]) == int(g["argmax"][j]) and out["z_map"][q] == float(g["z_map"][j]), q
+        assert abs(np.nanmax(ll[q]) - float(g["ll_max"][j])) < 1e-9 * abs(float(g["ll_max"][j]))
+    # (b) oracle on a coarse subset of the same sweep (every 10th sample: 1 000 per spectrum)
+    sub = np.arange(0, 10000, 10)
+    jobs = [(model, spectra[q], zs[sub]) for q in range(16)]
+    with mp.get_context("spawn").Pool(min(16, os.cpu_count() or 1)) as pool:
+        refs = pool.map(_zqso_oracle_one, jobs, chunksize=1)
+    for q, (rll, _) in enumerate(refs):
+        assert np.array_equal(np.isnan(ll[q][sub]), np.isnan(rll)), q
+        assert H.ll_err(ll[q][sub], rll) < 1e-9, q
