@@ -797,7 +797,8 @@ static int cat_consume(dla_catalogue* cat, int bi, dla_catalogue_outputs* o) {
   return 0;
 }
 
-static int cat_run(dla_catalogue* cat, const CatSource& src, const double* d_log_priors_in, dla_catalogue_outputs* o) {
+static int cat_run_pipeline(dla_catalogue* cat, const CatSource& src, const double* d_log_priors_in, dla_catalogue_outputs* o,
+                            int* open_ranges) {
   Runtime& rt = runtime();
   const size_t cap = src.max_n_raw;
   int rc = cat_ensure_workspace(cat, cap, !src.on_device, o);
@@ -812,6 +813,7 @@ static int cat_run(dla_catalogue* cat, const CatSource& src, const double* d_log
   // the copy stream must not run ahead of work queued before this call (log_priors upload, previous run)
   DLA_CUDA(cudaStreamWaitEvent(rt.copy_stream, cat->ev_call0, 0));
   nvtxRangePushA("dla_catalogue_run");
+  ++*open_ranges;
   for (int bi = 0; bi < std::min(2, nbatches); ++bi) {
     if (!src.on_device && (rc = cat_enqueue_upload(cat, src, bi))) return rc;
     if ((rc = cat_enqueue_prep(cat, src, bi, P, cap))) return rc;
@@ -820,6 +822,7 @@ static int cat_run(dla_catalogue* cat, const CatSource& src, const double* d_log
     char label[64];
     snprintf(label, sizeof(label), "batch %d (spectra %d..%d)", bi, bi * cat->B, std::min(src.Q, (bi + 1) * cat->B) - 1);
     nvtxRangePushA(label);
+    ++*open_ranges;
     if ((rc = cat_enqueue_compute(cat, bi, cap, o, d_log_priors_in))) return rc;
     if (bi >= 1 && (rc = cat_consume(cat, bi - 1, o))) return rc;
     if (bi + 2 < nbatches) {
@@ -827,9 +830,11 @@ static int cat_run(dla_catalogue* cat, const CatSource& src, const double* d_log
       if ((rc = cat_enqueue_prep(cat, src, bi + 2, P, cap))) return rc;
     }
     nvtxRangePop();
+    --*open_ranges;
   }
   if ((rc = cat_consume(cat, nbatches - 1, o))) return rc;
   nvtxRangePop();
+  --*open_ranges;
   // whole call on the library stream: kernels, descriptor uploads, result copies and host gaps
   DLA_CUDA(cudaEventRecord(cat->ev_call1, rt.stream));
   DLA_CUDA(cudaEventSynchronize(cat->ev_call1));
@@ -841,6 +846,21 @@ static int cat_run(dla_catalogue* cat, const CatSource& src, const double* d_log
   cat->launches = rt.launches - launches_before;
   rt.last_kernel_ms = cat->total_ms;
   return 0;
+}
+
+static int cat_run(dla_catalogue* cat, const CatSource& src, const double* d_log_priors_in, dla_catalogue_outputs* o) {
+  int open_ranges = 0;
+  const int rc = cat_run_pipeline(cat, src, d_log_priors_in, o, &open_ranges);
+  if (rc) {
+    // an error left batches in flight: nothing may still read the caller's host buffers or write the staging slots
+    // when this call returns (the error text of the first failure is kept)
+    Runtime& rt = runtime();
+    cudaStreamSynchronize(rt.copy_stream);
+    cudaStreamSynchronize(rt.stream);
+    cudaGetLastError();
+    while (open_ranges-- > 0) nvtxRangePop();
+  }
+  return rc;
 }
 
 extern "C" int dla_catalogue_run_staged(dla_catalogue* cat, dla_catalogue_outputs* o) {
