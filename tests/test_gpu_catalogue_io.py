@@ -91,6 +91,14 @@ def test_pipeline_many_batches_equals_single_batch(gpu):
     c = small.run_staged(keep_samples=False)
     for k in c:
         assert np.array_equal(a[k], c[k], equal_nan=True), k
+    # evaluation accounting: every sample of levels >= 1 is either evaluated or left out by the separation mask, and the
+    # mask count is exactly the number of NaNs the reference would have written over computed values
+    tm = small.last_timing()
+    S, md = 96, 4
+    assert np.all(a["status"] == 0)
+    assert tm["evaluations"] + tm["evaluations_masked"] == Q * (5 * S + 1)
+    assert tm["evaluations_masked"] == int(np.isnan(a["sample_log_likelihoods_dla"][:, :, 1:]).sum())
+    assert tm["evaluations_masked"] > 0 and tm["likelihood_flops"] > 0
 
 
 _WORKER = r"""
