@@ -445,7 +445,7 @@ static int cat_enqueue_prep(dla_catalogue* cat, const CatSource& src, int bi, co
 
 // ---- pipeline stage: size batch `bi`, write its descriptors, enqueue every kernel and the result read-back ------
 static int cat_enqueue_compute(dla_catalogue* cat, int bi, size_t cap, const dla_catalogue_outputs* o,
-                               const double* d_log_priors_in) {
+                               const double* d_log_priors_in, int* open_ranges) {
   Runtime& rt = runtime();
   CatSlot& sl = cat->slot[bi & 1];
   const int S = cat->S, md = cat->max_dlas, m = 2 + md, w = cat->params.width;
@@ -692,6 +692,10 @@ static int cat_enqueue_compute(dla_catalogue* cat, int bi, size_t cap, const dla
     return rc;
   DLA_CUDA(cudaEventRecord(sl.ev_v1, rt.stream));
   for (int level = 0; level < md; ++level) {
+    char lvl[32];
+    snprintf(lvl, sizeof(lvl), "level %d", level);
+    nvtxRangePushA(lvl);  // popped below; the error paths inside return with it open and cat_run pops what is left
+    ++*open_ranges;
     if (level > 0) {
       compact_level_kernel<<<nb, 1024, 0, rt.stream>>>(d_compact + (size_t)level * nb);
       DLA_LAUNCHED();
@@ -712,6 +716,8 @@ static int cat_enqueue_compute(dla_catalogue* cat, int bi, size_t cap, const dla
       evidence_level_kernel<<<nb, 1024, 0, rt.stream>>>(d_ev + (size_t)md * nb);
       DLA_LAUNCHED();
     }
+    nvtxRangePop();
+    --*open_ranges;
   }
   {
     dim3 grid(md, nb);
@@ -823,7 +829,7 @@ static int cat_run_pipeline(dla_catalogue* cat, const CatSource& src, const doub
     snprintf(label, sizeof(label), "batch %d (spectra %d..%d)", bi, bi * cat->B, std::min(src.Q, (bi + 1) * cat->B) - 1);
     nvtxRangePushA(label);
     ++*open_ranges;
-    if ((rc = cat_enqueue_compute(cat, bi, cap, o, d_log_priors_in))) return rc;
+    if ((rc = cat_enqueue_compute(cat, bi, cap, o, d_log_priors_in, open_ranges))) return rc;
     if (bi >= 1 && (rc = cat_consume(cat, bi - 1, o))) return rc;
     if (bi + 2 < nbatches) {
       if (!src.on_device && (rc = cat_enqueue_upload(cat, src, bi + 2))) return rc;
