@@ -160,6 +160,8 @@ typedef struct dla_catalogue_config {
   int keep_sample_likelihoods; /* write the (Q,S,max_dlas) / (Q,S) sample arrays */
 } dla_catalogue_config;
 
+/* The catalogue BORROWS `model`: it must stay alive until dla_catalogue_destroy (the Python binding keeps both in one
+ * object).  Sample arrays and uniforms are copied to the device by this call. */
 int dla_catalogue_create(const dla_model* model, const dla_params* params,
                          const dla_catalogue_config* config,
                          const double* dla_offset_samples, const double* dla_log_nhi_samples,
