@@ -429,6 +429,7 @@ def run_gpu_dla(args):
     sampler.start()
     launches0 = lib.dla_kernel_launch_count()
     dev_ms, lik_ms, voigt_ms, lik_flops = 0.0, 0.0, 0.0, 0.0
+    evals, evals_masked = 0, 0
     t_wall0 = time.perf_counter()
     for _ in range(args.steps):
         out = proc.run_staged(keep_samples=False)
@@ -437,6 +438,8 @@ def run_gpu_dla(args):
         lik_ms += tm["likelihood_ms"]
         voigt_ms += tm["voigt_ms"]
         lik_flops += tm["likelihood_flops"]
+        evals += tm["evaluations"]
+        evals_masked += tm["evaluations_masked"]
     barrier()
     wall_ms = 1e3 * (time.perf_counter() - t_wall0)
     clocks = sampler.stop()
@@ -483,7 +486,11 @@ def run_gpu_dla(args):
         "kernel_share_of_step": lik_ms / dev_ms if dev_ms > 0 else None,
         "voigt_share_of_step": voigt_ms / dev_ms if dev_ms > 0 else None,
         "whole_step_frac_of_peak": lik_flops / (dev_ms * 1e-3) / 1e12 / peak if dev_ms > 0 and peak > 0 else None,
-        "flops_per_evaluation": "472 n + 3.1e3 (SURVEY.md §8d); %d evaluations per spectrum" % (5 * c["S"] + 1),
+        "flops_per_evaluation": "472 n + 3.1e3 (SURVEY.md §8d), counted for the evaluations that are RUN: of the %d per "
+                                "spectrum the reference computes, the level >= 1 samples its separation test overwrites "
+                                "with NaN (dla_gp.py:164-177) are not evaluated" % (5 * c["S"] + 1),
+        "evaluations_per_spectrum": evals / float(Q * args.steps),
+        "evaluations_masked_per_spectrum": evals_masked / float(Q * args.steps),
     }
 
     line = {
